@@ -1,0 +1,130 @@
+/* vampnet_b200 — C ABI of the B200-native VampNet masked-token generation hot path.
+ *
+ * The reference (hugofloresgarcia/vampnet) is pure Python/PyTorch and has no FFI of its own; its
+ * boundary is the Python class surface.  These entry points are what a binding
+ * for that surface binds (INTEGRATION.md shows the ctypes stub); each cites the reference
+ * function it replaces.  Plain pointers and sizes only: device pointers are raw CUDA addresses,
+ * `stream` is a cudaStream_t passed as void*.  All functions return 0 on success, non-zero on
+ * error; vnb_last_error() returns a thread-local message.  Nothing here aborts the process.
+ *
+ * Handles are not thread-safe (the reference is called from one worker thread at a time:
+ * app.py:730 demo.queue()).
+ */
+#ifndef VAMPNET_B200_H
+#define VAMPNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VNB_ABI_VERSION 1
+
+typedef struct vnb_model vnb_model;
+
+/* Mirrors VampNet.__init__ (reference vampnet/modules/transformer.py:536-552). */
+typedef struct vnb_config {
+  int32_t n_heads;
+  int32_t n_layers;
+  int32_t n_codebooks;
+  int32_t n_conditioning_codebooks;
+  int32_t latent_dim; /* 8 */
+  int32_t d_model;    /* embedding_dim */
+  int32_t vocab_size; /* 1024; mask token id == vocab_size */
+} vnb_config;
+
+/* Packed weights, all DEVICE pointers owned by the caller and kept alive while the model exists.
+ * Packing (LoRA fold, weight-norm fold, bf16 rounding, row permutations) is done by the host
+ * side (vampnet_b200/modules/transformer.py: pack_weights). */
+typedef struct vnb_weights {
+  const float* emb_table;  /* (C, V+1, 8)  codec codebooks with the learned MASK row appended (layers.py:145-150) */
+  const float* emb_wt;     /* (8C, d)      embedding.out_proj.weight transposed (layers.py:132) */
+  const float* emb_b;      /* (d) */
+  const float* norm1;      /* (L, d)       norm_1.weight */
+  const void* wqkv;        /* (L, 3d, d)   bf16, rows = [w_qs | w_ks | w_vs] (transformer.py:109-114) */
+  const void* wo;          /* (L, d, d)    bf16, fc */
+  const float* norm3;      /* (L, d)       norm_3.weight */
+  const void* w1;          /* (L, 4d, d)   bf16, feed_forward.w_1 with rows interleaved per 256-row tile:
+                                           [128 value rows | 128 gate rows] (activations.py:33-35) */
+  const void* w2;          /* (L, d, 2d)   bf16, feed_forward.w_2 */
+  const float* norm_f;     /* (d)          transformer.norm.weight */
+  const void* wcls;        /* (Cp*V, d)    bf16, classifier g*v/|v| with rows permuted to c*V + p (transformer.py:634) */
+  const float* bcls;       /* (Cp*V)       permuted the same way */
+  const float* rel_bias;   /* (2*rel_sat+1, H) fp32: bias for clamp(key-query, -rel_sat, rel_sat) (transformer.py:123-209) */
+  int32_t rel_sat;
+} vnb_weights;
+
+/* Mirrors the keyword arguments of VampNet.generate that are live on this path
+ * (transformer.py:687-710; SURVEY.md §A.6 lists the dead ones).  The per-step schedule arrays
+ * are computed by the host with the reference's own fp32 expressions (mask.py:8-9,
+ * transformer.py:831-834, 903, 917-919) so that floor(gamma*N0) matches bit for bit. */
+typedef struct vnb_gen_params {
+  int32_t sampling_steps;
+  float temperature;        /* <=0 means softmax(logits) without scaling (transformer.py:1019-1023) */
+  const float* gamma;       /* host, [steps]: _gamma((i+1)/steps) as fp32 */
+  const float* temp_eff;    /* host, [steps]: mask_temperature * (1 - r_i) as fp32 */
+  const int32_t* do_sample; /* host, [steps]: (i/steps) <= sample_cutoff */
+  uint32_t seed_lo, seed_hi; /* Philox key */
+  int32_t use_graph;        /* 1: capture the whole loop once per shape and replay it as a CUDA graph */
+} vnb_gen_params;
+
+int32_t vnb_abi_version(void);
+const char* vnb_last_error(void);
+
+/* VampNet.__init__ + load (interface.py:27-50): builds tensor maps / workspace lazily per (B, T). */
+int32_t vnb_model_create(const vnb_config* cfg, const vnb_weights* w, vnb_model** out);
+void vnb_model_destroy(vnb_model* m);
+
+/* embedding.from_codes + VampNet.forward (layers.py:134-162, transformer.py:617-639).
+ * codes: (B, C, T) int64 device.  logits: (B, T*Cp, V) fp32 device, i.e. the reference's
+ * (B, V, T*Cp) output transposed (the layout generate() permutes to at transformer.py:849). */
+int32_t vnb_forward_codes(vnb_model* m, const int64_t* codes, int32_t B, int32_t T, float* logits, void* stream);
+/* VampNet.forward on caller-supplied latents (B, 8C, T) fp32 (transformer.py:617). */
+int32_t vnb_forward_latents(vnb_model* m, const float* latents, int32_t B, int32_t T, float* logits, void* stream);
+/* Debug tap: copy the fp32 residual stream (B*T, d) after the last layer of the last forward. */
+int32_t vnb_get_hidden(vnb_model* m, float* out, void* stream);
+
+/* VampNet.generate(return_signal=False) (transformer.py:686-946).
+ * z: (B, C, T) int64; mask: (B, C, T) int32 or NULL (default mask, transformer.py:749-751);
+ * out: (B, C, T) int64. */
+int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_t B, int32_t T,
+                     const vnb_gen_params* p, int64_t* out, void* stream);
+/* One sampling iteration on caller-supplied logits (B, S, V) fp32 — sample_from_logits +
+ * mask_by_random_topk + the where()s around them (transformer.py:849-932).  State is explicit:
+ * zflat (B, S) int32 in "t c" order (util.py:39) is updated in place; tokens_out (B, S) int32
+ * receives sampled_z; conf_out (B, S) fp32 receives the confidences (debug).
+ * n0: device pointer to the whole-batch initial mask count (transformer.py:766). */
+int32_t vnb_sample_step(const float* logits, int32_t* zflat, int32_t* tokens_out, float* conf_out,
+                        const int32_t* n0, int32_t B, int32_t S, int32_t V, int32_t mask_token, int32_t step,
+                        int32_t is_last, int32_t do_sample, float temperature, float gamma, float temp_eff,
+                        uint32_t seed_lo, uint32_t seed_hi, void* stream);
+
+/* ---- unit-level entry points (parity tests bisect with these) ------------------------------- */
+enum {
+  VNB_EPI_BF16 = 0,     /* out bf16 (M, N) */
+  VNB_EPI_QKV = 1,      /* cols < 2d -> qk bf16 (M, 2d); cols >= 2d -> vT bf16 (B, d, Tpad) */
+  VNB_EPI_RESID = 2,    /* out fp32 (M, N) += acc */
+  VNB_EPI_GEGLU = 3,    /* out bf16 (M, N/2) = value * gelu_tanh(gate) */
+  VNB_EPI_BIAS_F32 = 4  /* out fp32 (M, N) = acc + bias[n] */
+};
+/* out = A (M,K) bf16 row-major  x  W (N,K)^T bf16 row-major, fp32 accumulate in TMEM.
+ * N % 256 == 0, K % 64 == 0.  For VNB_EPI_QKV: out = qk, out2 = vT, T/Tpad describe the batch split. */
+int32_t vnb_op_gemm(int32_t epi, const void* A, const void* W, int32_t M, int32_t N, int32_t K, void* out,
+                    void* out2, const float* bias, int32_t T, int32_t Tpad, void* stream);
+/* y bf16 = w * x * rsqrt(mean(x^2) + eps)  (transformer.py:43-58) */
+int32_t vnb_op_rmsnorm(const float* x, const float* w, void* y, int32_t M, int32_t d, float eps, void* stream);
+/* Fused self-attention with relative-position bias (transformer.py:234-254).
+ * qk (B, T, 2d) bf16 [q | k], vT (B, d, Tpad) bf16, out (B, T, d) bf16, d = H*64. */
+int32_t vnb_op_attention(const void* qk, const void* vT, void* out, const float* rel_bias, int32_t rel_sat,
+                         int32_t B, int32_t T, int32_t Tpad, int32_t H, void* stream);
+/* x fp32 (B*T, d) = out_proj(from_codes(codes)) ; codes_btc (B, T, C) int32 (internal layout). */
+int32_t vnb_op_embed_codes(const int32_t* codes_btc, const float* table, const float* wt, const float* b, float* x,
+                           int32_t B, int32_t T, int32_t C, int32_t V1, int32_t d, void* stream);
+/* Naive SIMT GEMM used only to bisect the tcgen05 path in tests: out fp32 (M, N) = A x W^T. */
+int32_t vnb_dbg_gemm_ref(const void* A, const void* W, int32_t M, int32_t N, int32_t K, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAMPNET_B200_H */

@@ -1,0 +1,284 @@
+// vampnet_b200 — fused bidirectional self-attention with T5-style relative-position bias on the
+// sm_100a tensor cores.
+//
+// Replaces MultiHeadRelativeAttention.forward between the projections (reference
+// vampnet/modules/transformer.py:234-254): scores = q.k^T / sqrt(64) + bias[h, k - q]; softmax over
+// keys; out = P.v; heads merged as "b l (head v)".  The reference materialises (H,B,T,T) scores in
+// HBM three times per layer; here they live only in TMEM/registers.  The position bias
+// (compute_bias, :183-209) is Toeplitz in (k - q) and saturates beyond |k - q| >= sat, so it is a
+// (2*sat+1)-entry table per head held in shared memory.
+//
+// One CTA = one (batch, head, 128-query tile); key/value blocks of 64:
+//   warp 0      TMA producer (Q once; K_j and V^T_j through a 2-stage ring); owns the TMEM allocation
+//   warp 1      MMA issuer   S = Q.K_j^T (tcgen05.mma M128 N64 K16 x4) ; O += P_j.V_j (same shape)
+//   warps 2..5  softmax      one thread per query row: tcgen05.ld S -> scale+bias -> running max ->
+//                            exp2 -> bf16 P into 128B-swizzled smem (A operand of P.V) ; O stays in TMEM
+//                            and is rescaled in place only when a row's running max grows.
+// Roofline: tensor-bound in FLOPs (4*T^2*64 per (b,h)), but at d_head = 64 the per-block TMEM read
+// (128x64 fp32) and MUFU.EX2 cost as much as the two MMAs; see DESIGN.md.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vnb {
+
+constexpr int AQ = 128, AK = 64, DH = 64;
+constexpr int Q_BYTES = AQ * DH * 2;   // 16 KiB
+constexpr int K_BYTES = AK * DH * 2;   // 8 KiB
+constexpr int V_BYTES = DH * AK * 2;   // 8 KiB
+constexpr int P_BYTES = AQ * AK * 2;   // 16 KiB
+constexpr int ATT_MAX_SAT = 128;
+constexpr int ATT_SMEM_TILES = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + P_BYTES;  // 64 KiB
+constexpr int ATT_SMEM = ATT_SMEM_TILES + 1024 /*align*/ + (2 * ATT_MAX_SAT + 1) * 4 + 128 /*barriers*/;
+constexpr int ATT_THREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnArgs {
+  __nv_bfloat16* out;
+  const float* rel;
+  int sat, B, T, H, d;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmVT, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;          // 2 stages
+  uint8_t* sV = sK + 2 * K_BYTES;      // 2 stages
+  uint8_t* sP = sV + 2 * V_BYTES;
+  float* sBias = reinterpret_cast<float*>(sP + P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * ATT_MAX_SAT + 2);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nblk = (a.T + AK - 1) / AK;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmVT);
+    }
+    __syncwarp();
+    tmem_alloc<128>(tmem_slot);
+  }
+  // bias table for this head, pre-multiplied by log2(e)
+  for (int i = threadIdx.x; i < 2 * a.sat + 1; i += ATT_THREADS) sBias[i] = a.rel[i * a.H + h] * LOG2E;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // columns [0, 64)
+  const uint32_t tmem_O = tmem_base + 64;   // columns [64, 128)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Q_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, h * DH, q0, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1, 500 + st);
+        mbar_expect_tx(&kv_full[st], K_BYTES + V_BYTES);
+        tma_load_3d(sK + st * K_BYTES, &tmK, &kv_full[st], a.d + h * DH, j * AK, b);
+        tma_load_3d(sV + st * V_BYTES, &tmVT, &kv_full[st], j * AK, h * DH, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(AQ, AK);  // M=128, N=64 for both products
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      mbar_wait(q_full, 0, 510);
+      mbar_wait(&kv_full[0], 0, 511);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k)
+        umma_bf16(tmem_S, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(smem_u32(sK) + k * 32), idesc, k != 0);
+      umma_commit(s_full);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        mbar_wait(p_full, j & 1, 520);
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sV + st * V_BYTES);
+#pragma unroll
+        for (int k = 0; k < AK / 16; ++k)
+          umma_bf16(tmem_O, umma_desc_sw128(aP + k * 32), umma_desc_sw128(aV + k * 32), idesc, (j | k) != 0);
+        umma_commit(&kv_empty[st]);
+        umma_commit(o_full);
+        if (j + 1 < nblk) {
+          const int st2 = (j + 1) & 1;
+          mbar_wait(&kv_full[st2], ((j + 1) >> 1) & 1, 530 + st2);
+          tc_fence_after();
+          const uint32_t aK = smem_u32(sK + st2 * K_BYTES);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k)
+            umma_bf16(tmem_S, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc, k != 0);
+          umma_commit(s_full);
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warps (one thread per query row) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int q = q0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const float c = 0.125f * LOG2E;  // 1/sqrt(64) folded with log2(e)
+    const int sat = a.sat;
+    float m_ref = -INFINITY, l = 0.f;
+    uint8_t* prow = sP + row * 128;
+    const int sw = row & 7;
+
+    for (int j = 0; j < nblk; ++j) {
+      const int k0 = j * AK;
+      mbar_wait(s_full, j & 1, 540);
+      tc_fence_after();
+      uint32_t sr[64];
+      {
+        uint32_t t0[32], t1[32];
+        tmem_ld_x32(tmem_S + lane_off, t0);
+        tmem_ld_x32(tmem_S + lane_off + 32, t1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { sr[i] = t0[i]; sr[32 + i] = t1[i]; }
+      }
+      // scale + bias (+ mask of keys beyond T), all in the log2 domain
+      const int rel_lo = k0 - (q0 + AQ - 1), rel_hi = k0 + AK - 1 - q0;
+      float mx = -INFINITY;
+      if (rel_lo >= sat || rel_hi <= -sat) {
+        const float bconst = sBias[rel_lo >= sat ? 2 * sat : 0];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          float t = fmaf(__uint_as_float(sr[i]), c, bconst);
+          if (k0 + i >= a.T) t = -INFINITY;
+          sr[i] = __float_as_uint(t);
+          mx = fmaxf(mx, t);
+        }
+      } else {
+        const int base = k0 - q + sat;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          int idx = base + i;
+          idx = idx < 0 ? 0 : (idx > 2 * sat ? 2 * sat : idx);
+          float t = fmaf(__uint_as_float(sr[i]), c, sBias[idx]);
+          if (k0 + i >= a.T) t = -INFINITY;
+          sr[i] = __float_as_uint(t);
+          mx = fmaxf(mx, t);
+        }
+      }
+      const float m_new = fmaxf(m_ref, mx);
+      if (j > 0) {
+        // P.V of the previous block must have retired: P buffer is free and O is stable.
+        mbar_wait(o_full, (j - 1) & 1, 550);
+        tc_fence_after();
+        const bool grow = m_new > m_ref;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float alpha = fast_exp2(m_ref - m_new);  // 1 for rows whose max did not grow
+          uint32_t o[32];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            tmem_ld_x32(tmem_O + lane_off + hh * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tmem_O + lane_off + hh * 32, o);
+          }
+          tmem_wait_st();
+          l *= alpha;
+        }
+      }
+      m_ref = m_new;
+      float psum = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        float p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          p[i] = fast_exp2(__uint_as_float(sr[ch * 8 + i]) - m_ref);
+          psum += p[i];
+        }
+        uint4 w;
+        w.x = pack_bf16x2(p[0], p[1]);
+        w.y = pack_bf16x2(p[2], p[3]);
+        w.z = pack_bf16x2(p[4], p[5]);
+        w.w = pack_bf16x2(p[6], p[7]);
+        *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = w;
+      }
+      l += psum;
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- finalize: O / l -> bf16 -> (B, T, d) at [b, q, h*64 ..]
+    mbar_wait(o_full, (nblk - 1) & 1, 560);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* orow = a.out + (static_cast<size_t>(b) * a.T + q) * a.d + h * DH;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t o[32];
+      tmem_ld_x32(tmem_O + lane_off + hh * 32, o);
+      tmem_wait_ld();
+      if (q < a.T) {
+        uint4* o4 = reinterpret_cast<uint4*>(orow + hh * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+          o4[i] = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem_base);
+}
+
+cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ATT_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (p.sat > ATT_MAX_SAT || p.sat < 1) return cudaErrorInvalidValue;
+  AttnArgs a;
+  a.out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  a.rel = p.rel;
+  a.sat = p.sat; a.B = p.B; a.T = p.T; a.H = p.H; a.d = p.H * DH;
+  dim3 grid((p.T + AQ - 1) / AQ, p.H, p.B);
+  attention_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(p.tmQ, p.tmK, p.tmVT, a);
+  return cudaGetLastError();
+}
+
+}  // namespace vnb

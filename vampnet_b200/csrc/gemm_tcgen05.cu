@@ -1,0 +1,322 @@
+// vampnet_b200 — bf16 GEMM on the sm_100a tensor cores (tcgen05.mma, TMEM accumulators, TMA operands).
+//
+//   out = epilogue( A (M,K) row-major bf16  x  W (N,K)^T row-major bf16 ),  fp32 accumulation
+//
+// One kernel family covers every dense contraction of VampNet.forward (reference
+// vampnet/modules/transformer.py): QKV projection (:229-231), attention output projection (:255),
+// FFN up-projection with the GatedGELU fused (:81-83, activations.py:16-35), FFN down-projection
+// with the residual add fused (:84, :367) and the classifier (:632).
+//
+// Structure (one CTA per SM, persistent over output tiles of 128 x 256):
+//   warp 0       TMA producer   : 4-stage ring of {A 128x64, W 256x64} bf16 tiles, 128B-swizzled
+//   warp 1       MMA issuer     : one elected thread, tcgen05.mma M=128 N=256 K=16, 4 per k-block
+//   warp 2       TMEM allocator : 512 columns = two 128x256 fp32 accumulators (double buffered)
+//   warps 4..7   epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> fused op -> global
+// The epilogue of tile i overlaps the mainloop of tile i+1 through the two accumulators.
+//
+// Roofline: tensor-bound.  Algorithmic work = 2*M*N*K flop per launch; bytes (A+W+out) are a few
+// MB against > 10 GFLOP, far right of the ridge.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vnb {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmArgs {
+  int M, N, K;
+  int epi;
+  void* out;          // see VNB_EPI_*
+  void* out2;         // vT for EPI_QKV
+  const float* bias;  // EPI_BIAS_F32
+  int T, Tpad;        // EPI_QKV: rows m = b*T + t
+  int d2;             // EPI_QKV: 2*d_model (column where V starts)
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))   (activations.py:16-26); tanh(y) = 1 - 2/(1+exp(2y))
+  const float y = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float e = __expf(2.0f * y);
+  const float t = 1.0f - __fdividef(2.0f, 1.0f + e);
+  return 0.5f * x * (1.0f + t);
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int row, int col0, bool row_ok,
+                                               const uint32_t (&v)[32], const uint32_t (&v2)[32], int b_idx,
+                                               int t_idx) {
+  if (!row_ok) return;
+  if constexpr (EPI == VNB_EPI_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<size_t>(row) * g.N + col0;
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 w;
+      w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+      w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+      w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+      w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+      o4[i] = w;
+    }
+  } else if constexpr (EPI == VNB_EPI_QKV) {
+    if (col0 < g.d2) {  // q | k : row-major (M, 2d)
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<size_t>(row) * g.d2 + col0;
+      uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+        w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+        w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+        w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+        o4[i] = w;
+      }
+    } else {  // v : transposed (B, d, Tpad) so that attention's P.V B-operand is K-major over keys
+      const int d = g.N - g.d2;
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out2) +
+                         (static_cast<size_t>(b_idx) * d + (col0 - g.d2)) * g.Tpad + t_idx;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[static_cast<size_t>(j) * g.Tpad] = __float2bfloat16_rn(__uint_as_float(v[j]));
+    }
+  } else if constexpr (EPI == VNB_EPI_RESID) {
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<size_t>(row) * g.N + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 x = o4[i];
+      x.x += __uint_as_float(v[4 * i + 0]);
+      x.y += __uint_as_float(v[4 * i + 1]);
+      x.z += __uint_as_float(v[4 * i + 2]);
+      x.w += __uint_as_float(v[4 * i + 3]);
+      o4[i] = x;
+    }
+  } else if constexpr (EPI == VNB_EPI_GEGLU) {
+    // v = value columns, v2 = gate columns of the same output features (weights interleaved at pack time)
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<size_t>(row) * (g.N / 2) + col0;
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(v[8 * i + j]) * gelu_tanh(__uint_as_float(v2[8 * i + j]));
+      uint4 w;
+      w.x = pack_bf16x2(r[0], r[1]);
+      w.y = pack_bf16x2(r[2], r[3]);
+      w.z = pack_bf16x2(r[4], r[5]);
+      w.w = pack_bf16x2(r[6], r[7]);
+      o4[i] = w;
+    }
+  } else {  // VNB_EPI_BIAS_F32
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<size_t>(row) * g.N + col0);
+    const float4* b4 = reinterpret_cast<const float4*>(g.bias + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = __ldg(b4 + i);
+      float4 x;
+      x.x = __uint_as_float(v[4 * i + 0]) + b.x;
+      x.y = __uint_as_float(v[4 * i + 1]) + b.y;
+      x.z = __uint_as_float(v[4 * i + 2]) + b.z;
+      x.w = __uint_as_float(v[4 * i + 3]) + b.w;
+      o4[i] = x;
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms are 1024 B: align the tile ring to 1024.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (g.M + BM - 1) / BM;
+  const int num_n = g.N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = g.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one elected lane of each of the 4 epilogue warps
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % num_m) * BM;
+        const int n0 = (tile / num_m) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle span
+            umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile % num_m) * BM;
+      const int n0 = (tile / num_m) * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < g.M;
+      int b_idx = 0, t_idx = 0;
+      if constexpr (EPI == VNB_EPI_QKV) {
+        b_idx = row / g.T;
+        t_idx = row - b_idx * g.T;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      if constexpr (EPI == VNB_EPI_GEGLU) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32], v2[32];
+          tmem_ld_x32(t_addr + c * 32, v);
+          tmem_ld_x32(t_addr + 128 + c * 32, v2);
+          tmem_wait_ld();
+          epilogue_chunk<EPI>(g, row, (n0 >> 1) + c * 32, row_ok, v, v2, b_idx, t_idx);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_addr + c * 32, v);
+          tmem_wait_ld();
+          epilogue_chunk<EPI>(g, row, n0 + c * 32, row_ok, v, v, b_idx, t_idx);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+
+template <int EPI>
+static cudaError_t launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GEMM_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, g);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t st) {
+  GemmArgs g;
+  g.M = p.M; g.N = p.N; g.K = p.K; g.epi = p.epi; g.out = p.out; g.out2 = p.out2; g.bias = p.bias;
+  g.T = p.T; g.Tpad = p.Tpad; g.d2 = p.d2;
+  switch (p.epi) {
+    case VNB_EPI_BF16: return launch_epi<VNB_EPI_BF16>(p.tmA, p.tmB, g, st);
+    case VNB_EPI_QKV: return launch_epi<VNB_EPI_QKV>(p.tmA, p.tmB, g, st);
+    case VNB_EPI_RESID: return launch_epi<VNB_EPI_RESID>(p.tmA, p.tmB, g, st);
+    case VNB_EPI_GEGLU: return launch_epi<VNB_EPI_GEGLU>(p.tmA, p.tmB, g, st);
+    case VNB_EPI_BIAS_F32: return launch_epi<VNB_EPI_BIAS_F32>(p.tmA, p.tmB, g, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Naive SIMT GEMM (test-only bisecting aid; never on the product path).
+__global__ void gemm_ref_kernel(const __nv_bfloat16* A, const __nv_bfloat16* W, int M, int N, int K, float* out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k)
+    acc += __bfloat162float(A[static_cast<size_t>(m) * K + k]) * __bfloat162float(W[static_cast<size_t>(n) * K + k]);
+  out[static_cast<size_t>(m) * N + n] = acc;
+}
+cudaError_t launch_gemm_ref(const void* A, const void* W, int M, int N, int K, float* out, cudaStream_t st) {
+  dim3 grid((N + 127) / 128, M);
+  gemm_ref_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(A),
+                                        reinterpret_cast<const __nv_bfloat16*>(W), M, N, K, out);
+  return cudaGetLastError();
+}
+
+}  // namespace vnb

@@ -1,0 +1,84 @@
+// vampnet_b200 — internal launcher declarations shared by the .cu translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vampnet_b200.h"
+
+namespace vnb {
+
+// ---- TMA tensor maps (driver entry point fetched at run time; no link-time libcuda dependency) ----
+// 2-D bf16 row-major (rows, cols) with a (box_rows x 64) box, 128B swizzle.
+bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                  uint32_t box_cols);
+// 3-D bf16 (batch, rows, cols) row-major with row pitch `pitch_elems`; box (1, box_rows, 64), 128B swizzle.
+bool make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
+                  uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols);
+const char* tmap_error();
+
+// ---- GEMM ----
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  int M = 0, N = 0, K = 0, epi = 0;
+  void* out = nullptr;
+  void* out2 = nullptr;
+  const float* bias = nullptr;
+  int T = 1, Tpad = 1, d2 = 0;
+};
+// Fills the tensor maps; A (M,K) bf16, W (N,K) bf16.
+bool make_gemm_plan(GemmPlan* p, int epi, const void* A, const void* W, int M, int N, int K, void* out, void* out2,
+                    const float* bias, int T, int Tpad, int d2);
+cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t st);
+cudaError_t launch_gemm_ref(const void* A, const void* W, int M, int N, int K, float* out, cudaStream_t st);
+
+// ---- attention ----
+struct AttnPlan {
+  CUtensorMap tmQ;   // (B, T, 2d)  box (1, 128 rows, 64 cols)
+  CUtensorMap tmK;   // (B, T, 2d)  box (1, 64 rows, 64 cols)
+  CUtensorMap tmVT;  // (B, d, Tpad) box (1, 64 rows, 64 cols)
+  void* out = nullptr;         // (B, T, d) bf16
+  const float* rel = nullptr;  // (2*sat+1, H)
+  int sat = 0, B = 0, T = 0, Tpad = 0, H = 0;
+};
+bool make_attn_plan(AttnPlan* p, const void* qk, const void* vT, void* out, const float* rel, int sat, int B, int T,
+                    int Tpad, int H);
+cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st);
+
+// ---- elementwise / gather ----
+cudaError_t launch_rmsnorm(const float* x, const float* w, void* y_bf16, int M, int d, float eps, cudaStream_t st);
+// codes_btc (B*T, C) int32  -> x (B*T, d) fp32
+cudaError_t launch_embed_codes(const int32_t* codes_btc, const float* table, const float* wt, const float* b, float* x,
+                               int M, int C, int V1, int d, cudaStream_t st);
+// latents (B, K, T) fp32 -> x (B*T, d) fp32
+cudaError_t launch_embed_latents(const float* lat, const float* wt, const float* b, float* x, int B, int T, int K,
+                                 int d, cudaStream_t st);
+
+// ---- generate-loop state kernels ----
+// z (B,C,T) int64, mask (B,C,T) int32|null -> zcur (B,T,C) int32 (masked), zorig (B,T,C) int32; n0 += count(MASK)
+cudaError_t launch_gen_init(const int64_t* z, const int32_t* mask, int32_t* zcur, int32_t* zorig, int32_t* n0, int B,
+                            int C, int T, int ncc, int mask_token, cudaStream_t st);
+// tokens (B, T, Cp) int32 + zorig cond -> out (B, C, T) int64
+cudaError_t launch_gen_finish(const int32_t* tokens, const int32_t* zorig, int64_t* out, int B, int C, int T, int ncc,
+                              cudaStream_t st);
+
+// per-step dynamic scalars, read from DEVICE memory so that a captured CUDA graph can be replayed with
+// new temperatures / seeds (the schedule values are computed on the host with the reference's fp32
+// expressions: mask.py:8-9, transformer.py:831-834, 917-919)
+struct SampleDyn {
+  float inv_temp, gamma, temp_eff;
+  int do_sample, is_last, step;
+  uint32_t seed_lo, seed_hi;
+};
+struct SampleArgs {
+  const float* logits;  // (B*S, V)
+  int32_t* zcur;        // (B, T, C) int32, predicted codebooks at c >= ncc ; updated in place by the remask kernel
+  const int32_t* zorig; // (B, T, C) int32 or null (then conditioning codebooks are left untouched)
+  int32_t* tokens;      // (B, T, Cp) sampled_z
+  float* conf;          // (B, S)
+  const int32_t* n0;    // device scalar
+  int B, T, C, ncc, V, mask_token;
+};
+cudaError_t launch_sample_step_dev(const SampleArgs& a, const SampleDyn* dyn_dev, cudaStream_t st);
+
+}  // namespace vnb

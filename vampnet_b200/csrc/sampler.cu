@@ -1,0 +1,243 @@
+// vampnet_b200 — one sampling iteration of VampNet.generate, after the logits exist
+// (reference vampnet/modules/transformer.py:849-932): sample_from_logits (:952-1034; typical_filter's
+// result is discarded by the reference and so is absent here), the where()s that keep known tokens,
+// the cosine-schedule count (:903-913, mask.py:8-9) and mask_by_random_topk (:1038-1074).
+//
+// Two kernels, both HBM-bound:
+//   sample_rows_kernel   one warp per (batch, position): reads the 1024 logits of a STILL-MASKED
+//                        position once (32 per lane, float4), warp-shuffle max / sum-exp / Gumbel-max
+//                        arg-max with counter-based Philox noise, writes token + confidence.
+//                        Known positions cost 4 bytes.  Algorithmic bytes: V*4 per masked position.
+//   remask_kernel        one CTA per batch row: exact k-th order statistic of the S confidences by a
+//                        4-pass radix select (what sort()[k] yields in the reference), then
+//                        z <- where(conf < cut, MASK, token).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vnb {
+
+// ---- Philox4x32-10 (Salmon et al.); stream layout documented in oracle/philox.py ----------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x >> 8) + 0.5f) * 5.9604644775390625e-08f; }
+__device__ __forceinline__ float gumbel(float u) { return -logf(-logf(u)); }
+
+using SampleDynDev = SampleDyn;
+
+struct SampleStatic {
+  const float* logits;
+  int32_t* zcur;
+  const int32_t* zorig;
+  int32_t* tokens;
+  float* conf;
+  const int32_t* n0;
+  int B, T, C, ncc, V, mask_token;
+};
+
+__global__ void __launch_bounds__(256) sample_rows_kernel(const SampleStatic a, const SampleDynDev* __restrict__ dynp) {
+  const SampleDynDev dyn = *dynp;
+  const int Cp = a.C - a.ncc;
+  const int S = a.T * Cp;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= a.B * S) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / S, s = row - b * S;
+  const int t = s / Cp, cp = s - t * Cp;
+  const int zi = a.zcur[(static_cast<size_t>(b) * a.T + t) * a.C + a.ncc + cp];
+  if (zi != a.mask_token) {  // known token: kept, never re-masked (transformer.py:893-900)
+    if (lane == 0) {
+      a.tokens[row] = zi;
+      a.conf[row] = INFINITY;
+    }
+    return;
+  }
+  const int V = a.V;  // 1024 -> 8 float4 per lane
+  const float4* lr = reinterpret_cast<const float4*>(a.logits + static_cast<size_t>(row) * V);
+  constexpr int MAXV4 = 8;
+  float4 x[MAXV4];
+  const int n4 = V >> 7;  // float4s per lane
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    if (i < n4) {
+      float4 v = lr[i * 32 + lane];
+      x[i] = v;
+      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+  }
+  // arg-max of the raw logits (greedy) or of logits*inv_t + Gumbel (sampling), lowest index on ties
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  if (dyn.do_sample) {
+#pragma unroll
+    for (int i = 0; i < MAXV4; ++i) {
+      if (i < n4) {
+        const uint32_t i4 = i * 32 + lane;
+        uint32_t r[4];
+        philox4x32_10(i4, static_cast<uint32_t>(row), static_cast<uint32_t>(dyn.step), 0u, dyn.seed_lo, dyn.seed_hi, r);
+        const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float sc = __fadd_rn(__fmul_rn(xs[j], dyn.inv_temp), gumbel(u01(r[j])));
+          if (sc > best) { best = sc; best_i = static_cast<int>(i4 * 4 + j); }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < MAXV4; ++i) {
+      if (i < n4) {
+        const int i4 = i * 32 + lane;
+        const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (xs[j] > best) { best = xs[j]; best_i = i4 * 4 + j; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  // softmax probability of the chosen token: probs = softmax(logits * inv_t) (transformer.py:1019-1023)
+  mx = warp_max(mx);
+  const float m = __fmul_rn(mx, dyn.inv_temp);  // inv_t > 0 so the max commutes
+  float se = 0.f, xt = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    if (i < n4) {
+      const int i4 = i * 32 + lane;
+      const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float sx = __fmul_rn(xs[j], dyn.inv_temp);
+        se += expf(sx - m);
+        if (i4 * 4 + j == best_i) xt = sx;
+      }
+    }
+  }
+  se = warp_sum(se);
+  xt = warp_sum(xt);  // exactly one lane contributed
+  if (lane == 0) {
+    const float p = expf(xt - m) / se;
+    uint32_t r[4];
+    philox4x32_10(static_cast<uint32_t>(s), static_cast<uint32_t>(b), static_cast<uint32_t>(dyn.step), 1u, dyn.seed_lo,
+                  dyn.seed_hi, r);
+    // confidence = log p + temperature * Gumbel (transformer.py:1055-1057)
+    const float cf = __fadd_rn(logf(p), __fmul_rn(dyn.temp_eff, gumbel(u01(r[0]))));
+    a.tokens[row] = best_i;
+    a.conf[row] = cf;
+  }
+}
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(1024) remask_kernel(const SampleStatic a, const SampleDynDev* __restrict__ dynp) {
+  const SampleDynDev dyn = *dynp;
+  const int Cp = a.C - a.ncc;
+  const int S = a.T * Cp;
+  const int b = blockIdx.x;
+  const float* conf = a.conf + static_cast<size_t>(b) * S;
+  const int32_t* tok = a.tokens + static_cast<size_t>(b) * S;
+  int32_t* zrow = a.zcur + static_cast<size_t>(b) * a.T * a.C;
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_maskbits;
+  __shared__ int s_rank, s_cnt;
+
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  // masked positions in this row before the update (mask.sum(dim=-1), transformer.py:906-913)
+  int local = 0;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const int t = s / Cp, cp = s - t * Cp;
+    local += (zrow[t * a.C + a.ncc + cp] == a.mask_token);
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_cnt, local);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // num_to_mask = floor(gamma(r) * N0) in fp32 (transformer.py:903), clamped unless last step
+    int n = static_cast<int>(floorf(__fmul_rn(dyn.gamma, static_cast<float>(*a.n0))));
+    if (!dyn.is_last) {
+      int up = s_cnt - 1;
+      if (n > up) n = up;
+      if (n < 1) n = 1;
+    }
+    if (n > S - 1) n = S - 1;
+    if (n < 0) n = 0;
+    s_rank = n;
+    s_prefix = 0;
+    s_maskbits = 0;
+  }
+  __syncthreads();
+  // radix select: key of the element at sorted position n (ascending)
+  for (int pass = 3; pass >= 0; --pass) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix, mb = s_maskbits;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+      const uint32_t k = f2key(conf[s]);
+      if ((k & mb) == prefix) atomicAdd(&hist[(k >> (8 * pass)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int rank = s_rank;
+      unsigned cum = 0;
+      int bkt = 0;
+      for (; bkt < 255; ++bkt) {
+        if (cum + hist[bkt] > static_cast<unsigned>(rank)) break;
+        cum += hist[bkt];
+      }
+      s_rank = rank - static_cast<int>(cum);
+      s_prefix = prefix | (static_cast<unsigned>(bkt) << (8 * pass));
+      s_maskbits = mb | (0xFFu << (8 * pass));
+    }
+    __syncthreads();
+  }
+  const uint32_t cut = s_prefix;
+  // z_masked = where(conf < cut, MASK, sampled_z) (transformer.py:922-924); conditioning codebooks are
+  // re-attached from the ORIGINAL z (transformer.py:930-932)
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const int t = s / Cp, cp = s - t * Cp;
+    const bool rm = f2key(conf[s]) < cut;
+    zrow[t * a.C + a.ncc + cp] = rm ? a.mask_token : tok[s];
+  }
+  if (a.zorig != nullptr && a.ncc > 0) {
+    const int32_t* zo = a.zorig + static_cast<size_t>(b) * a.T * a.C;
+    for (int i = threadIdx.x; i < a.T * a.ncc; i += blockDim.x) {
+      const int t = i / a.ncc, c = i - t * a.ncc;
+      zrow[t * a.C + c] = zo[t * a.C + c];
+    }
+  }
+}
+
+cudaError_t launch_sample_step_dev(const SampleArgs& s, const SampleDyn* dyn_dev, cudaStream_t st) {
+  SampleStatic a;
+  a.logits = s.logits; a.zcur = s.zcur; a.zorig = s.zorig; a.tokens = s.tokens; a.conf = s.conf; a.n0 = s.n0;
+  a.B = s.B; a.T = s.T; a.C = s.C; a.ncc = s.ncc; a.V = s.V; a.mask_token = s.mask_token;
+  if (s.V % 128 != 0 || s.V > 1024) return cudaErrorInvalidValue;
+  const int rows = s.B * s.T * (s.C - s.ncc);
+  sample_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(a, dyn_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  remask_kernel<<<s.B, 1024, 0, st>>>(a, dyn_dev);
+  return cudaGetLastError();
+}
+
+}  // namespace vnb
