@@ -9,6 +9,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "kernels.h"
@@ -124,18 +125,15 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct GraphKey {
+struct GraphKey {  // graphs bake pointers, so generate() stages z/mask/out in workspace-owned buffers
   int steps;
   bool has_mask;
-  const void* z; const void* mask; const void* out;  // graphs bake pointers: key on them
-  bool operator<(const GraphKey& o) const {
-    return std::tie(steps, has_mask, z, mask, out) < std::tie(o.steps, o.has_mask, o.z, o.mask, o.out);
-  }
+  bool operator<(const GraphKey& o) const { return std::tie(steps, has_mask) < std::tie(o.steps, o.has_mask); }
 };
 
 struct Workspace {
   int B = 0, T = 0, Tpad = 0, M = 0;
-  DevBuf x, y, qk, vT, att, h, logits, zcur, zorig, tokens, conf, n0, dyn;
+  DevBuf x, y, qk, vT, att, h, logits, zcur, zorig, tokens, conf, n0, dyn, z_in, mask_in, z_out;
   std::vector<GemmPlan> qkv, wo, up, down;
   GemmPlan cls;
   AttnPlan attn;
@@ -177,6 +175,9 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   CK(ws->conf.alloc(M * Cp * 4));
   CK(ws->n0.alloc(4, true));
   CK(ws->dyn.alloc(sizeof(SampleDyn) * vnb_model::kMaxSteps));
+  CK(ws->z_in.alloc(M * c.n_codebooks * 8));
+  CK(ws->mask_in.alloc(M * c.n_codebooks * 4));
+  CK(ws->z_out.alloc(M * c.n_codebooks * 8));
   const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(m->w.wqkv);
   const __nv_bfloat16* wo = reinterpret_cast<const __nv_bfloat16*>(m->w.wo);
   const __nv_bfloat16* w1 = reinterpret_cast<const __nv_bfloat16*>(m->w.w1);
@@ -333,7 +334,13 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   CK(cudaMemcpyAsync(ws->dyn.p, dyn.data(), sizeof(SampleDyn) * steps, cudaMemcpyHostToDevice, st));
   if (!p->use_graph) return enqueue_generate(m, ws, z, mask, steps, out, st);
 
-  GraphKey key{steps, mask != nullptr, z, mask, out};
+  const size_t nz = static_cast<size_t>(B) * m->cfg.n_codebooks * T;
+  CK(cudaMemcpyAsync(ws->z_in.p, z, nz * 8, cudaMemcpyDeviceToDevice, st));
+  if (mask) CK(cudaMemcpyAsync(ws->mask_in.p, mask, nz * 4, cudaMemcpyDeviceToDevice, st));
+  const int64_t* gz = ws->z_in.as<int64_t>();
+  const int32_t* gmask = mask ? ws->mask_in.as<int32_t>() : nullptr;
+  int64_t* gout = ws->z_out.as<int64_t>();
+  GraphKey key{steps, mask != nullptr};
   auto it = ws->graphs.find(key);
   if (it == ws->graphs.end()) {
     cudaStream_t cap;
@@ -341,7 +348,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) { cudaStreamDestroy(cap); return fail("begin capture: %s", cudaGetErrorString(e)); }
-    int rc = enqueue_generate(m, ws, z, mask, steps, out, cap);
+    int rc = enqueue_generate(m, ws, gz, gmask, steps, gout, cap);
     e = cudaStreamEndCapture(cap, &graph);
     cudaStreamDestroy(cap);
     if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
@@ -357,6 +364,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
     it = ws->graphs.emplace(key, exec).first;
   }
   CK(cudaGraphLaunch(it->second, st));
+  CK(cudaMemcpyAsync(out, ws->z_out.p, nz * 8, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
