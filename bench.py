@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — VampNet masked-token generation hot path on B200 (contract in the task statement).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (oracle port of the reference)
+    torchrun ... bench.py --gpus N ...                        # N>1: one rank per GPU, weak scaling
+
+Workload (BASELINE.json configs[2], the configuration the metric "coarse+c2f" is quoted on; fits one GPU):
+one "step" = coarse VampNet.generate (4 codebooks, d=1280, 20 layers, 12 sampling steps) followed by
+coarse-to-fine VampNet.generate (14 codebooks, 4 conditioning, 16 layers, 24 sampling steps, unchunked) on
+B=32 clips of T=768 frames per GPU, default sampling parameters (temperature 1, mask_temperature 10.5),
+random-init weights, synthetic random codes, periodic prompt every 7th frame.  value = codec tokens/s =
+N*B*T*14 / time.  Real-time factor = N*B*T*768/44100 / time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_FRAMES = 768
+BATCH = 32
+COARSE = dict(n_heads=20, n_layers=20, n_codebooks=4, n_conditioning_codebooks=0, embedding_dim=1280)
+C2F = dict(n_heads=20, n_layers=16, n_codebooks=14, n_conditioning_codebooks=4, embedding_dim=1280)
+COARSE_STEPS, C2F_STEPS = 12, 24
+HOP, SR = 768, 44100
+METRIC = "codec tokens/sec (coarse 12 steps + c2f 24 steps generate, T=768, 44.1 kHz)"
+
+
+def fwd_flops(cfg, T):
+    """Algorithmic FLOPs of one sequence-forward: T*[L*(20d^2 + 4Td) + 2*(8C)*d + 2*d*V*Cp]."""
+    d, L, Cn = cfg["embedding_dim"], cfg["n_layers"], cfg["n_codebooks"]
+    Cp = Cn - cfg["n_conditioning_codebooks"]
+    return T * (L * (20 * d * d + 4 * T * d) + 2 * 8 * Cn * d + 2 * d * 1024 * Cp)
+
+
+def family_flops(cfg, T, B, steps):
+    d, L, Cn = cfg["embedding_dim"], cfg["n_layers"], cfg["n_codebooks"]
+    Cp = Cn - cfg["n_conditioning_codebooks"]
+    M = B * T
+    per = {
+        "gemm_qkv": 2 * M * 3 * d * d * L, "gemm_attn_out": 2 * M * d * d * L, "gemm_ffn_up": 2 * M * 4 * d * d * L,
+        "gemm_ffn_down": 2 * M * 2 * d * d * L, "gemm_classifier": 2 * M * d * 1024 * Cp,
+        "attention": 4 * B * T * T * d * L,
+    }
+    return {k: v * steps for k, v in per.items()}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(threads):
+    """Bounded sample of the same workload on the host cores through the oracle port of the reference
+    (oracle/vampnet_oracle.py, fp32 like the reference's CPU path): one coarse and one c2f sampling iteration
+    (forward + sample + remask) at B=1, T=768, extrapolated to 12 + 24 iterations per clip."""
+    from oracle import vampnet_oracle as vo
+    torch.set_num_threads(threads)
+    res = {}
+    g = torch.Generator().manual_seed(0)
+    for tag, cfgd in (("coarse", COARSE), ("c2f", C2F)):
+        cfg = vo.OracleConfig(**cfgd)
+        sd = vo.make_state_dict(cfg, seed=0)
+        orc = vo.OracleVampNet(cfg, sd, "fp32")
+        cb = vo.make_codebooks(cfg.n_codebooks, seed=1)
+        z = torch.randint(0, 1024, (1, cfg.n_codebooks, T_FRAMES), generator=g)
+        mask = torch.ones_like(z)
+        mask[:, :, ::7] = 0
+        mask[:, :cfg.n_conditioning_codebooks] = 0
+        t0 = time.perf_counter()
+        orc.generate(cb, z, mask, _sampling_steps=1, seed=0, rng="torch")
+        res[tag] = time.perf_counter() - t0
+        del orc, sd
+    clip_s = COARSE_STEPS * res["coarse"] + C2F_STEPS * res["c2f"]
+    return T_FRAMES * 14 / clip_s, res
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        v, parts = cpu_sample(threads)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            vals.append((v, dt))
+    v = statistics.mean(x[0] for x in vals)
+    sample = ("per step: 1 coarse + 1 c2f sampling iteration at B=1,T=768 through the oracle port (fp32, "
+              f"{threads} threads), extrapolated to 12+24 iterations per clip")
+    line = {
+        "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(x[1] for x in vals), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "rtf": v / 14 * HOP / SR,
+        "config": {"workload": "BASELINE.json configs[2] (coarse 12 + c2f 24 steps, T=768), bounded CPU sample at B=1",
+                   "seq_len": T_FRAMES, "global_batch": 1},
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+class _Codec:
+    def __init__(self, cb):
+        import types
+        self.quantizer = types.SimpleNamespace(quantizers=[types.SimpleNamespace(
+            codebook=types.SimpleNamespace(weight=cb[i])) for i in range(cb.shape[0])])
+        self.sample_rate, self.hop_length = SR, HOP
+
+
+def broadcast_weights(models, world):
+    """NCCL over NVLink: rank 0's weights to every rank, one flat blob per model (the only collective on this path)."""
+    if world == 1:
+        return
+    import torch.distributed as dist
+    for m in models:
+        params = [p for p in m.parameters()]
+        flat = torch.cat([p.data.reshape(-1).float() for p in params])
+        dist.broadcast(flat, src=0)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.data.copy_(flat[off:off + n].view_as(p))
+            off += n
+        m._invalidate()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="clips per GPU (default = the named config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    if args.warmup < 3:
+        args.warmup = 3
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback on the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from vampnet_b200 import _lib
+    from vampnet_b200.modules.transformer import VampNet
+
+    lib = _lib.lib()
+    torch.manual_seed(1234)
+    with torch.device(dev):
+        coarse = VampNet(**COARSE)
+        c2f = VampNet(**C2F)
+        cb = torch.randn(14, 1024, 8)
+    broadcast_weights([coarse, c2f], world)
+    if world > 1:
+        dist.broadcast(cb, src=0)
+    codec = _Codec(cb)
+
+    B, T = args.batch, T_FRAMES
+    g = torch.Generator().manual_seed(100 + rank)  # every rank vamps its own clips
+    z_host = torch.randint(0, 1024, (B, 14, T), generator=g).pin_memory()
+    mask_host = torch.ones(B, 14, T, dtype=torch.int64)
+    mask_host[:, :, ::7] = 0
+    mask_host = mask_host.pin_memory()
+    z_dev = z_host.to(dev)
+    mask_dev = mask_host.to(dev)
+    mask_c2f_dev = mask_dev.clone()
+    mask_c2f_dev[:, :4] = 0  # conditioning codebooks are never masked (interface.py:355-357)
+
+    def step(z, mask, mask_c2f, seed):
+        zc = coarse.generate(codec, start_tokens=z[:, :4].contiguous(), mask=mask[:, :4].contiguous(),
+                             _sampling_steps=COARSE_STEPS, return_signal=False, seed=seed)
+        zin = torch.cat([zc, z[:, 4:]], dim=1)
+        return c2f.generate(codec, start_tokens=zin, mask=mask_c2f, _sampling_steps=C2F_STEPS, return_signal=False,
+                            seed=seed + 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        out = step(z_dev, mask_dev, mask_c2f_dev, 10 + 2 * i)
+    torch.cuda.synchronize()
+    assert not (out == 1024).any(), "mask tokens survived generate()"
+
+    # ---- timed region: inputs resident in HBM, production path (CUDA-graph replay) ----
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.3)
+    launches0 = lib.vnb_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step(z_dev, mask_dev, mask_c2f_dev, 100 + 2 * i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.vnb_launch_count() - launches0
+    clk = clocks.stop()
+
+    # ---- end to end: host (pinned) inputs, H2D + D2H inside the timed region, public generate() API ----
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        zd = z_host.to(dev, non_blocking=True)
+        md = mask_host.to(dev, non_blocking=True)
+        mc = md.clone()
+        mc[:, :4] = 0
+        res_host = step(zd, md, mc, 200 + 2 * i).cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d = z_host.numel() * 8 + mask_host.numel() * 8
+    d2h = res_host.numel() * 8
+
+    # max over ranks
+    tms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = tms.tolist()
+
+    # ---- per-kernel-family device time (CUDA events around every launch; graph bypassed) ----
+    fam_ms = {k: 0.0 for k in _lib.FAMILIES}
+    fam_n = {k: 0 for k in _lib.FAMILIES}
+    fl = {}
+    for model, cfgd, nsteps in ((coarse, COARSE, COARSE_STEPS), (c2f, C2F, C2F_STEPS)):
+        for k, v in family_flops(cfgd, T, B, nsteps).items():
+            fl[k] = fl.get(k, 0) + v
+    for model in (coarse, c2f):
+        _lib.check(lib.vnb_profile_begin(model._handle))
+    step(z_dev, mask_dev, mask_c2f_dev, 300)
+    torch.cuda.synchronize()
+    for model in (coarse, c2f):
+        a = (C.c_float * len(_lib.FAMILIES))()
+        n = (C.c_int32 * len(_lib.FAMILIES))()
+        _lib.check(lib.vnb_profile_end(model._handle, a, n, len(_lib.FAMILIES)))
+        for i, k in enumerate(_lib.FAMILIES):
+            fam_ms[k] += a[i]
+            fam_n[k] += n[i]
+    prof_total = sum(fam_ms.values())
+    gemm_keys = [k for k in _lib.FAMILIES if k.startswith("gemm")]
+    gemm_ms = sum(fam_ms[k] for k in gemm_keys)
+    gemm_fl = sum(fl[k] for k in gemm_keys)
+    gemm_n = sum(fam_n[k] for k in gemm_keys)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)  # kernel timed inside a long step -> sustained figure
+    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {
+        "kernel": "gemm_tcgen05_kernel (all epilogues: qkv, attn-out+residual, ffn-up+GEGLU, ffn-down+residual, classifier+bias)",
+        "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+        "traffic": None,
+        "flops_per_launch": gemm_fl / max(gemm_n, 1), "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
+        "share_of_step": gemm_ms / prof_total if prof_total else None,
+        "breakdown_ms": {k: round(fam_ms[k], 3) for k in _lib.FAMILIES},
+        "breakdown_tflops": {k: (fl[k] / (fam_ms[k] * 1e-3) / 1e12 if fam_ms.get(k) else None) for k in fl},
+        "profiled_step_ms": prof_total,
+    }
+
+    if rank == 0:
+        tokens = world * B * T * 14 * args.steps
+        value = tokens / (ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "rtf": world * B * T * HOP / SR * args.steps / (ms * 1e-3),
+            "tflops": world * (fwd_flops(COARSE, T) * COARSE_STEPS + fwd_flops(C2F, T) * C2F_STEPS) * B * args.steps
+                      / (ms * 1e-3) / 1e12,
+            "config": {"workload": "BASELINE.json configs[2]: coarse generate 12 steps (4 codebooks, 20 layers) -> c2f "
+                                   "generate 24 steps (14 codebooks, 16 layers), unchunked, d=1280, default sampling",
+                       "global_batch": world * B, "per_gpu_batch": B, "seq_len": T, "parallelism": f"dp{world} (clips)",
+                       "l2": "working set per step (2.4 GB bf16 weights + >1 GB logits) far exceeds the 126 MB L2",
+                       "weights": "random-init, NCCL-broadcast from rank 0", "cuda_graph": True},
+            "clocks": clk,
+            "e2e": {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms / args.steps,
+                    "api": "VampNet.generate(coarse) -> VampNet.generate(c2f) with pinned host tensors in, host tensor out"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, parts = cpu_sample(threads)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
+                "sample": (f"1 coarse + 1 c2f sampling iteration at B=1,T=768 via the oracle port (fp32): "
+                           f"{parts['coarse']:.2f}s + {parts['c2f']:.2f}s, extrapolated to 12+24 iterations per clip")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

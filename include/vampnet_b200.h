@@ -100,6 +100,19 @@ int32_t vnb_sample_step(const float* logits, int32_t* zflat, int32_t* tokens_out
                         int32_t is_last, int32_t do_sample, float temperature, float gamma, float temp_eff,
                         uint32_t seed_lo, uint32_t seed_hi, void* stream);
 
+/* ---- measurement hooks (bench.py) --------------------------------------------------------------
+ * vnb_launch_count: kernels launched by this library so far in this process (a graph replay adds the
+ * number of kernel nodes it contains).
+ * vnb_profile_begin/end: between the two calls every launch of forward/generate is bracketed by CUDA
+ * events on the launching stream (graph replay is bypassed so that the events can be recorded);
+ * end() returns the summed device time and launch count per kernel family:
+ *   0 embed, 1 rmsnorm, 2 gemm_qkv, 3 attention, 4 gemm_attn_out, 5 gemm_ffn_up, 6 gemm_ffn_down,
+ *   7 gemm_classifier, 8 sample+remask, 9 state init/finish. */
+#define VNB_NUM_FAMILIES 10
+uint64_t vnb_launch_count(void);
+int32_t vnb_profile_begin(vnb_model* m);
+int32_t vnb_profile_end(vnb_model* m, float* ms_per_family, int32_t* launches_per_family, int32_t n_families);
+
 /* ---- unit-level entry points (parity tests bisect with these) ------------------------------- */
 enum {
   VNB_EPI_BF16 = 0,     /* out bf16 (M, N) */

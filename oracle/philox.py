@@ -11,7 +11,8 @@ Stream layout (must match sampler.cu):
   token noise  : counter = (v // 4, b*S + s, step, 0), output lane v % 4
   remask noise : counter = (s, b, step, 1), output lane 0
   key          = (seed_lo, seed_hi)
-  uniform      = ((x >> 8) + 0.5) * 2**-24     -> strictly inside (0, 1), exact in fp32
+  uniform      = ((x >> 9) + 0.5) * 2**-23     -> strictly inside (0, 1), exact in fp32
+                 (24 bits + 0.5 needs 25 mantissa bits and would round up to 1.0)
 """
 from __future__ import annotations
 
@@ -48,7 +49,7 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def to_uniform(x: np.ndarray) -> np.ndarray:
-    return ((x >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24)
+    return ((x >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
 
 
 def uniform_bsv(key, step: int, B: int, S: int, V: int) -> np.ndarray:

@@ -12,6 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvampnet_b200.so")
 
 EPI_BF16, EPI_QKV, EPI_RESID, EPI_GEGLU, EPI_BIAS_F32 = range(5)
+FAMILIES = ("embed", "rmsnorm", "gemm_qkv", "attention", "gemm_attn_out", "gemm_ffn_up", "gemm_ffn_down",
+            "gemm_classifier", "sample_remask", "state")
 
 
 class Config(C.Structure):
@@ -46,6 +48,9 @@ _SIGS = {
     "vnb_get_hidden": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vnb_generate": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(GenParams),
                                  C.c_void_p, C.c_void_p]),
+    "vnb_launch_count": (C.c_uint64, []),
+    "vnb_profile_begin": (C.c_int32, [C.c_void_p]),
+    "vnb_profile_end": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
     "vnb_sample_step": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                     C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]),

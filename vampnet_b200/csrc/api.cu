@@ -138,14 +138,40 @@ struct Workspace {
   GemmPlan cls;
   AttnPlan attn;
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<GraphKey, unsigned long long> graph_kernels;
   ~Workspace() { for (auto& kv : graphs) cudaGraphExecDestroy(kv.second); }
 };
 
 }  // namespace vnb
 
+namespace vnb {
+enum { FAM_EMBED = 0, FAM_RMSNORM, FAM_GEMM_QKV, FAM_ATTN, FAM_GEMM_O, FAM_GEMM_UP, FAM_GEMM_DOWN, FAM_GEMM_CLS,
+       FAM_SAMPLE, FAM_STATE, FAM_COUNT };
+static unsigned long long g_launches = 0;  // kernels launched by this library (graph replays add their node count)
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> fam;  // family of the launch that FOLLOWS event i
+  size_t used = 0;
+  ~Profiler() { for (auto e : pool) cudaEventDestroy(e); }
+  void mark(int family, cudaStream_t st) {
+    if (!on) return;
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+      pool.push_back(e);
+      fam.push_back(-1);
+    }
+    fam[used] = family;
+    cudaEventRecord(pool[used++], st);
+  }
+};
+}  // namespace vnb
+
 struct vnb_model {
   vnb_config cfg;
   vnb_weights w;
+  vnb::Profiler prof;
   std::map<std::pair<int, int>, std::unique_ptr<vnb::Workspace>> ws;
   vnb::Workspace* last = nullptr;
   static constexpr int kMaxSteps = 256;
@@ -205,24 +231,32 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   return 0;
 }
 
+#define LAUNCH(fam_, expr)        \
+  do {                            \
+    m->prof.mark((fam_), st);     \
+    CK(expr);                     \
+    ++g_launches;                 \
+  } while (0)
+
 // x already holds the embedded input; runs the L layers + final norm + classifier into `logits`.
 static int run_stack(vnb_model* m, Workspace* ws, float* logits, cudaStream_t st) {
   const vnb_config& c = m->cfg;
   const int d = c.d_model;
   const float eps = 1e-6f;
   for (int l = 0; l < c.n_layers; ++l) {
-    CK(launch_rmsnorm(ws->x.as<float>(), m->w.norm1 + static_cast<size_t>(l) * d, ws->y.p, ws->M, d, eps, st));
-    CK(launch_gemm(ws->qkv[l], st));
-    CK(launch_attention(ws->attn, st));
-    CK(launch_gemm(ws->wo[l], st));
-    CK(launch_rmsnorm(ws->x.as<float>(), m->w.norm3 + static_cast<size_t>(l) * d, ws->y.p, ws->M, d, eps, st));
-    CK(launch_gemm(ws->up[l], st));
-    CK(launch_gemm(ws->down[l], st));
+    LAUNCH(FAM_RMSNORM, launch_rmsnorm(ws->x.as<float>(), m->w.norm1 + static_cast<size_t>(l) * d, ws->y.p, ws->M, d, eps, st));
+    LAUNCH(FAM_GEMM_QKV, launch_gemm(ws->qkv[l], st));
+    LAUNCH(FAM_ATTN, launch_attention(ws->attn, st));
+    LAUNCH(FAM_GEMM_O, launch_gemm(ws->wo[l], st));
+    LAUNCH(FAM_RMSNORM, launch_rmsnorm(ws->x.as<float>(), m->w.norm3 + static_cast<size_t>(l) * d, ws->y.p, ws->M, d, eps, st));
+    LAUNCH(FAM_GEMM_UP, launch_gemm(ws->up[l], st));
+    LAUNCH(FAM_GEMM_DOWN, launch_gemm(ws->down[l], st));
   }
-  CK(launch_rmsnorm(ws->x.as<float>(), m->w.norm_f, ws->y.p, ws->M, d, eps, st));
+  LAUNCH(FAM_RMSNORM, launch_rmsnorm(ws->x.as<float>(), m->w.norm_f, ws->y.p, ws->M, d, eps, st));
   GemmPlan cls = ws->cls;
   cls.out = logits;
-  CK(launch_gemm(cls, st));
+  LAUNCH(FAM_GEMM_CLS, launch_gemm(cls, st));
+  m->prof.mark(-1, st);
   return 0;
 }
 
@@ -262,9 +296,9 @@ int32_t vnb_forward_codes(vnb_model* m, const int64_t* codes, int32_t B, int32_t
   if (get_workspace(m, B, T, &ws)) return 1;
   const vnb_config& c = m->cfg;
   // (B,C,T) int64 -> (B,T,C) int32, no masking (mask = zeros)
-  CK(launch_gen_init(codes, nullptr, ws->zcur.as<int32_t>(), ws->zorig.as<int32_t>(), ws->n0.as<int32_t>(), B,
+  LAUNCH(FAM_STATE, launch_gen_init(codes, nullptr, ws->zcur.as<int32_t>(), ws->zorig.as<int32_t>(), ws->n0.as<int32_t>(), B,
                      c.n_codebooks, T, /*ncc=*/c.n_codebooks, c.vocab_size, st));
-  CK(launch_embed_codes(ws->zcur.as<int32_t>(), m->w.emb_table, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), ws->M,
+  LAUNCH(FAM_EMBED, launch_embed_codes(ws->zcur.as<int32_t>(), m->w.emb_table, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), ws->M,
                         c.n_codebooks, c.vocab_size + 1, c.d_model, st));
   m->last = ws;
   return run_stack(m, ws, logits, st);
@@ -275,7 +309,7 @@ int32_t vnb_forward_latents(vnb_model* m, const float* latents, int32_t B, int32
   Workspace* ws;
   if (get_workspace(m, B, T, &ws)) return 1;
   const vnb_config& c = m->cfg;
-  CK(launch_embed_latents(latents, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), B, T, c.n_codebooks * 8, c.d_model, st));
+  LAUNCH(FAM_EMBED, launch_embed_latents(latents, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), B, T, c.n_codebooks * 8, c.d_model, st));
   m->last = ws;
   return run_stack(m, ws, logits, st);
 }
@@ -290,7 +324,7 @@ static int enqueue_generate(vnb_model* m, Workspace* ws, const int64_t* z, const
                             cudaStream_t st) {
   const vnb_config& c = m->cfg;
   const int ncc = c.n_conditioning_codebooks;
-  CK(launch_gen_init(z, mask, ws->zcur.as<int32_t>(), ws->zorig.as<int32_t>(), ws->n0.as<int32_t>(), ws->B, c.n_codebooks,
+  LAUNCH(FAM_STATE, launch_gen_init(z, mask, ws->zcur.as<int32_t>(), ws->zorig.as<int32_t>(), ws->n0.as<int32_t>(), ws->B, c.n_codebooks,
                      ws->T, ncc, c.vocab_size, st));
   SampleArgs sa;
   sa.logits = ws->logits.as<float>();
@@ -301,12 +335,14 @@ static int enqueue_generate(vnb_model* m, Workspace* ws, const int64_t* z, const
   sa.n0 = ws->n0.as<int32_t>();
   sa.B = ws->B; sa.T = ws->T; sa.C = c.n_codebooks; sa.ncc = ncc; sa.V = c.vocab_size; sa.mask_token = c.vocab_size;
   for (int i = 0; i < steps; ++i) {
-    CK(launch_embed_codes(ws->zcur.as<int32_t>(), m->w.emb_table, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), ws->M,
+    LAUNCH(FAM_EMBED, launch_embed_codes(ws->zcur.as<int32_t>(), m->w.emb_table, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), ws->M,
                           c.n_codebooks, c.vocab_size + 1, c.d_model, st));
     if (run_stack(m, ws, ws->logits.as<float>(), st)) return 1;
-    CK(launch_sample_step_dev(sa, ws->dyn.as<SampleDyn>() + i, st));
+    LAUNCH(FAM_SAMPLE, launch_sample_step_dev(sa, ws->dyn.as<SampleDyn>() + i, st));
+    ++g_launches;  // sample step = two kernels
   }
-  CK(launch_gen_finish(ws->tokens.as<int32_t>(), ws->zorig.as<int32_t>(), out, ws->B, c.n_codebooks, ws->T, ncc, st));
+  LAUNCH(FAM_STATE, launch_gen_finish(ws->tokens.as<int32_t>(), ws->zorig.as<int32_t>(), out, ws->B, c.n_codebooks, ws->T, ncc, st));
+  m->prof.mark(-1, st);
   return 0;
 }
 
@@ -332,7 +368,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   }
   // pageable source: the runtime stages it before returning, so `dyn` may die at scope exit
   CK(cudaMemcpyAsync(ws->dyn.p, dyn.data(), sizeof(SampleDyn) * steps, cudaMemcpyHostToDevice, st));
-  if (!p->use_graph) return enqueue_generate(m, ws, z, mask, steps, out, st);
+  if (!p->use_graph || m->prof.on) return enqueue_generate(m, ws, z, mask, steps, out, st);
 
   const size_t nz = static_cast<size_t>(B) * m->cfg.n_codebooks * T;
   CK(cudaMemcpyAsync(ws->z_in.p, z, nz * 8, cudaMemcpyDeviceToDevice, st));
@@ -348,7 +384,10 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) { cudaStreamDestroy(cap); return fail("begin capture: %s", cudaGetErrorString(e)); }
+    const unsigned long long before = g_launches;
     int rc = enqueue_generate(m, ws, gz, gmask, steps, gout, cap);
+    const unsigned long long in_graph = g_launches - before;
+    g_launches = before;
     e = cudaStreamEndCapture(cap, &graph);
     cudaStreamDestroy(cap);
     if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
@@ -360,11 +399,37 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
     if (ws->graphs.size() >= 16) {  // bound the cache
       for (auto& kv : ws->graphs) cudaGraphExecDestroy(kv.second);
       ws->graphs.clear();
+      ws->graph_kernels.clear();
     }
     it = ws->graphs.emplace(key, exec).first;
+    ws->graph_kernels[key] = in_graph;
   }
   CK(cudaGraphLaunch(it->second, st));
+  g_launches += ws->graph_kernels[key];
   CK(cudaMemcpyAsync(out, ws->z_out.p, nz * 8, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+uint64_t vnb_launch_count(void) { return g_launches; }
+
+int32_t vnb_profile_begin(vnb_model* m) {
+  m->prof.used = 0;
+  m->prof.on = true;
+  return 0;
+}
+int32_t vnb_profile_end(vnb_model* m, float* ms_per_family, int32_t* launches_per_family, int32_t n_families) {
+  m->prof.on = false;
+  for (int i = 0; i < n_families; ++i) { ms_per_family[i] = 0.f; launches_per_family[i] = 0; }
+  if (m->prof.used < 2) return 0;
+  CK(cudaEventSynchronize(m->prof.pool[m->prof.used - 1]));
+  for (size_t i = 0; i + 1 < m->prof.used; ++i) {
+    const int f = m->prof.fam[i];
+    if (f < 0 || f >= n_families) continue;
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, m->prof.pool[i], m->prof.pool[i + 1]));
+    ms_per_family[f] += ms;
+    launches_per_family[f] += 1;
+  }
   return 0;
 }
 
