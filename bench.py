@@ -103,6 +103,24 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
+def host_threads():
+    """Threads the process may actually use: min(os.cpu_count(), affinity, cgroup cpu.max quota).  The GPU boxes
+    report 128 logical CPUs but cap the container at 16 (cpu.max 1600000/100000); 128 torch threads on a
+    16-CPU quota run ~15x slower than 16 threads."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_sample(threads):
     """Bounded sample of the same workload on the host cores through the oracle port of the reference
     (oracle/vampnet_oracle.py, fp32 like the reference's CPU path): one coarse and one c2f sampling iteration
@@ -131,7 +149,7 @@ def cpu_sample(threads):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     vals = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -352,7 +370,7 @@ def main():
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = host_threads()
             v, parts = cpu_sample(threads)
             line["cpu_baseline"] = {
                 "value": v, "unit": "tokens/s", "cores": threads, "kind": "port",

@@ -137,6 +137,26 @@ int32_t vnb_op_embed_codes(const int32_t* codes_btc, const float* table, const f
 /* Naive SIMT GEMM used only to bisect the tcgen05 path in tests: out fp32 (M, N) = A x W^T. */
 int32_t vnb_dbg_gemm_ref(const void* A, const void* W, int32_t M, int32_t N, int32_t K, float* out, void* stream);
 
+/* ---- codec (DAC family; reference call sites: interface.py:223 codec.encode, transformer.py:671-675
+ *      codec.quantizer.from_latents + codec.decode).  fp32, (B, C, T) channels-first. ------------------------
+ * Generic 1-D convolution with the Snake activation fused on the input:
+ *   y[b, co, q*out_stride + out_off] = bias[co] + sum_ci sum_j w[co, ci, j] * act(x[b, ci, q*stride + j*dil - pad])
+ *                                      (+ residual) (tanh)
+ * q in [0, nq).  snake_alpha (Cin) or NULL; residual (same shape as y) or NULL.  A ConvTranspose1d with stride s
+ * is s launches of the K=2, dil=-1 form with out_stride = s (one per output phase). */
+int32_t vnb_codec_conv1d(const float* x, const float* w, const float* bias, const float* snake_alpha,
+                         const float* residual, float* y, int32_t B, int32_t Cin, int32_t Tin, int32_t Cout,
+                         int32_t Tout, int32_t K, int32_t stride, int32_t dil, int32_t pad, int32_t out_stride,
+                         int32_t out_off, int32_t nq, int32_t do_tanh, void* stream);
+/* Residual vector quantiser.  mode 0 encode: in_f = z (B,D,T) -> codes (B,L,T) int64, zq (B,D,T), latents (B,8L,T).
+ * mode 1 from_latents: in_f = latents (B,8L,T) -> zq.  mode 2 from_codes: in_codes (B,L,T) -> zq.
+ * win (L,8,D), bin (L,8), wout (L,D,8), bout (L,D), cb (L,V,8) raw and cbn (L,V,8) L2-normalised codebooks. */
+int32_t vnb_codec_rvq(int32_t mode, const float* in_f, const int64_t* in_codes, const float* win, const float* bin,
+                      const float* wout, const float* bout, const float* cb, const float* cbn, int64_t* codes, float* zq,
+                      float* latents, int32_t B, int32_t D, int32_t T, int32_t L, int32_t V, void* stream);
+/* internal helper exported for the other translation units */
+int32_t vnb_set_error_cuda(const char* what, int32_t cuda_error);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,303 @@
+"""DAC-family neural codec on the sm_100a kernels.
+
+Provides what the reference takes from ``lac.model.lac.LAC`` (imported "as DAC", reference
+vampnet/interface.py:16):  DAC.load, .preprocess, .encode(...)["codes"], .decode(z)["audio"],
+.quantizer.from_latents, .quantizer.from_codes, .quantizer.quantizers[i].codebook.weight,
+.sample_rate, .hop_length  (call sites: interface.py:70, 179, 189, 215, 223; transformer.py:671-675;
+layers.py:145).  ``lac`` is an un-vendored, unpinned third-party fork of the Descript Audio Codec whose
+source and checkpoints are not available here; the architecture below is the published DAC (encoder
+dim 64, strides (2,4,8,12) -> hop 768, 14 x 1024 x 8 RVQ, decoder dim 1536) with hyper-parameters read
+from the checkpoint's metadata when one is loaded.  Parameter names follow the oracle / HF layout
+(encoder.block.{i}.res_unit{r}.conv1.weight ...); weight-norm pairs (weight_g / weight_v) are folded
+on load.
+
+All compute goes through the C ABI (vnb_codec_conv1d, vnb_codec_rvq); there is no torch fallback.
+"""
+from __future__ import annotations
+
+import math
+from pathlib import Path
+from typing import Dict
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class _Params(nn.Module):
+    """Nested parameter holder addressed by dotted names."""
+
+    def add(self, dotted: str, tensor: torch.Tensor):
+        head, _, rest = dotted.partition(".")
+        if not rest:
+            self.register_parameter(head, nn.Parameter(tensor, requires_grad=False))
+            return
+        if head not in self._modules:
+            self.add_module(head, _Params())
+        self._modules[head].add(rest, tensor)
+
+    def get(self, dotted: str) -> torch.Tensor:
+        obj = self
+        for part in dotted.split("."):
+            obj = obj._modules[part] if part in obj._modules else obj._parameters[part]
+        return obj
+
+
+def _layout(cfg) -> Dict[str, tuple]:
+    """name -> shape of every tensor of the codec."""
+    sh = {}
+    d = cfg["encoder_dim"]
+
+    def conv(n, co, ci, k):
+        sh[n + ".weight"], sh[n + ".bias"] = (co, ci, k), (co,)
+
+    def res(n, c):
+        sh[n + ".snake1.alpha"] = (c,)
+        conv(n + ".conv1", c, c, 7)
+        sh[n + ".snake2.alpha"] = (c,)
+        conv(n + ".conv2", c, c, 1)
+
+    conv("encoder.conv1", d, 1, 7)
+    for i, s in enumerate(cfg["encoder_rates"]):
+        for r in range(3):
+            res(f"encoder.block.{i}.res_unit{r + 1}", d)
+        sh[f"encoder.block.{i}.snake1.alpha"] = (d,)
+        conv(f"encoder.block.{i}.conv1", 2 * d, d, 2 * s)
+        d *= 2
+    sh["encoder.snake1.alpha"] = (d,)
+    conv("encoder.conv2", cfg["latent_dim"], d, 3)
+    for i in range(cfg["n_codebooks"]):
+        conv(f"quantizer.quantizers.{i}.in_proj", cfg["codebook_dim"], cfg["latent_dim"], 1)
+        conv(f"quantizer.quantizers.{i}.out_proj", cfg["latent_dim"], cfg["codebook_dim"], 1)
+        sh[f"quantizer.quantizers.{i}.codebook.weight"] = (cfg["codebook_size"], cfg["codebook_dim"])
+    c = cfg["decoder_dim"]
+    conv("decoder.conv1", c, cfg["latent_dim"], 7)
+    for i, s in enumerate(cfg["decoder_rates"]):
+        sh[f"decoder.block.{i}.snake1.alpha"] = (c,)
+        sh[f"decoder.block.{i}.conv_t1.weight"], sh[f"decoder.block.{i}.conv_t1.bias"] = (c, c // 2, 2 * s), (c // 2,)
+        for r in range(3):
+            res(f"decoder.block.{i}.res_unit{r + 1}", c // 2)
+        c //= 2
+    sh["decoder.snake1.alpha"] = (c,)
+    conv("decoder.conv2", 1, c, 7)
+    return sh
+
+
+class _Quantizer:
+    """codec.quantizer: .quantizers[i].codebook.weight, from_latents, from_codes, forward (encode)."""
+
+    def __init__(self, codec: "DAC"):
+        self._codec = codec
+
+    @property
+    def quantizers(self):
+        return list(self._codec.params._modules["quantizer"]._modules["quantizers"]._modules.values())
+
+    def _rvq(self, mode, in_f=None, in_codes=None):
+        c = self._codec
+        pk = c._packed()
+        src = in_f if in_f is not None else in_codes
+        B, T = src.shape[0], src.shape[-1]
+        dev = src.device
+        D, L, V = c.latent_dim, c.n_codebooks, c.codebook_size
+        if mode == 1:
+            L = in_f.shape[1] // c.codebook_dim
+        elif mode == 2:
+            L = in_codes.shape[1]
+        zq = torch.empty(B, D, T, device=dev, dtype=torch.float32)
+        codes = torch.empty(B, L, T, device=dev, dtype=torch.int64) if mode == 0 else None
+        lat = torch.empty(B, L * c.codebook_dim, T, device=dev, dtype=torch.float32) if mode == 0 else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().vnb_codec_rvq(mode, _lib.ptr(in_f), _lib.ptr(in_codes), _lib.ptr(pk["win"]),
+                                                _lib.ptr(pk["bin"]), _lib.ptr(pk["wout"]), _lib.ptr(pk["bout"]),
+                                                _lib.ptr(pk["cb"]), _lib.ptr(pk["cbn"]), _lib.ptr(codes), _lib.ptr(zq),
+                                                _lib.ptr(lat), B, D, T, L, V, _lib.stream_ptr(dev)))
+        return zq, codes, lat
+
+    def __call__(self, z):
+        zq, codes, lat = self._rvq(0, in_f=z.float().contiguous())
+        return zq, codes, lat
+
+    def from_latents(self, latents: torch.Tensor):
+        """(B, 8*L, T) -> (z_q, quantised latents): re-quantise each 8-d chunk then out_proj and sum."""
+        latents = latents.float().contiguous()
+        zq, _, _ = self._rvq(1, in_f=latents)
+        return zq, latents
+
+    def from_codes(self, codes: torch.Tensor):
+        codes = codes.to(torch.int64).contiguous()
+        zq, _, _ = self._rvq(2, in_codes=codes)
+        return zq, None, codes
+
+
+class DAC(nn.Module):
+    def __init__(self, encoder_dim: int = 64, encoder_rates=(2, 4, 8, 12), latent_dim: int = None,
+                 decoder_dim: int = 1536, decoder_rates=None, n_codebooks: int = 14, codebook_size: int = 1024,
+                 codebook_dim: int = 8, sample_rate: int = 44100, **_ignored):
+        super().__init__()
+        self.encoder_dim = encoder_dim
+        self.encoder_rates = tuple(encoder_rates)
+        self.decoder_rates = tuple(decoder_rates) if decoder_rates is not None else tuple(reversed(self.encoder_rates))
+        self.latent_dim = latent_dim if latent_dim is not None else encoder_dim * 2 ** len(self.encoder_rates)
+        self.decoder_dim = decoder_dim
+        self.n_codebooks = n_codebooks
+        self.codebook_size = codebook_size
+        self.codebook_dim = codebook_dim
+        self.sample_rate = sample_rate
+        self.hop_length = int(math.prod(self.encoder_rates))
+        self._cfg = dict(encoder_dim=encoder_dim, encoder_rates=self.encoder_rates, latent_dim=self.latent_dim,
+                         decoder_dim=decoder_dim, decoder_rates=self.decoder_rates, n_codebooks=n_codebooks,
+                         codebook_size=codebook_size, codebook_dim=codebook_dim)
+        self.params = _Params()
+        g = torch.Generator().manual_seed(0)
+        for name, shape in _layout(self._cfg).items():
+            if name.endswith(".alpha"):
+                t = torch.ones(shape)
+            elif name.endswith(".bias"):
+                t = torch.zeros(shape)
+            else:
+                fan = shape[1] * (shape[2] if len(shape) == 3 else 1)
+                t = torch.randn(shape, generator=g) / math.sqrt(max(fan, 1))
+            self.params.add(name, t)
+        self.quantizer = _Quantizer(self)
+        self._pack = None
+        self.eval()
+
+    # ---- state ---------------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._pack = None
+        return super()._apply(fn, *a, **k)
+
+    def load_flat(self, weights: Dict[str, torch.Tensor]):
+        """Load a flat {dotted name: tensor} dict (oracle / HF naming).  weight_g / weight_v pairs are folded."""
+        weights = dict(weights)
+        for k in [k for k in weights if k.endswith(".weight_v")]:
+            base = k[: -len("_v")]
+            v, gk = weights.pop(k), base + "_g"
+            g = weights.pop(gk)
+            weights[base] = v * (g / v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1))))
+        own = _layout(self._cfg)
+        missing = [k for k in own if k not in weights]
+        if missing:
+            raise KeyError(f"codec weights missing {len(missing)} tensors, e.g. {missing[:3]}")
+        with torch.no_grad():
+            for k, shape in own.items():
+                t = weights[k].float().reshape(shape)
+                self.params.get(k).data.copy_(t.to(self.params.get(k).device))
+        self._pack = None
+        return self
+
+    @classmethod
+    def load(cls, location, *_, **__):
+        """audiotools BaseModel.load layout: {'state_dict': ..., 'metadata': {'kwargs': {...}}} (interface.py:70)."""
+        blob = torch.load(str(Path(location)), map_location="cpu", weights_only=False)
+        kwargs = dict(blob.get("metadata", {}).get("kwargs", {}))
+        model = cls(**kwargs)
+        sd = {k[len("params."):] if k.startswith("params.") else k: v for k, v in blob["state_dict"].items()}
+        model.load_flat(sd)
+        return model
+
+    @property
+    def device(self):
+        return self.params.get("encoder.conv1.weight").device
+
+    def _packed(self):
+        if self._pack is not None:
+            return self._pack
+        if self.device.type != "cuda":
+            raise RuntimeError("vampnet_b200.codec.DAC runs only on a CUDA (sm_100a) device; there is no CPU fallback")
+        P = self.params.get
+        L = self.n_codebooks
+        q = "quantizer.quantizers."
+        pk = {
+            "win": torch.stack([P(f"{q}{i}.in_proj.weight").squeeze(-1) for i in range(L)]).contiguous(),
+            "bin": torch.stack([P(f"{q}{i}.in_proj.bias") for i in range(L)]).contiguous(),
+            "wout": torch.stack([P(f"{q}{i}.out_proj.weight").squeeze(-1) for i in range(L)]).contiguous(),
+            "bout": torch.stack([P(f"{q}{i}.out_proj.bias") for i in range(L)]).contiguous(),
+            "cb": torch.stack([P(f"{q}{i}.codebook.weight") for i in range(L)]).contiguous(),
+        }
+        pk["cbn"] = torch.nn.functional.normalize(pk["cb"], dim=-1).contiguous()
+        # ConvTranspose1d(k=2s, stride s) as s two-tap convolutions: Wp[r][co][ci][j] = W[ci][co][r + j*s]
+        for i, s in enumerate(self.decoder_rates):
+            w = P(f"decoder.block.{i}.conv_t1.weight")  # (cin, cout, 2s)
+            pk[f"convt{i}"] = torch.stack([w[:, :, r::s].permute(1, 0, 2) for r in range(s)]).contiguous()
+        self._pack = pk
+        return pk
+
+    # ---- kernels -------------------------------------------------------------------------------
+    def _conv(self, x, name, K, stride=1, dil=1, pad=0, alpha=None, resid=None, tanh=False, out=None):
+        w, b = self.params.get(name + ".weight"), self.params.get(name + ".bias")
+        B, Cin, Tin = x.shape
+        Cout = w.shape[0]
+        Tout = (Tin + 2 * pad - dil * (K - 1) - 1) // stride + 1
+        y = out if out is not None else torch.empty(B, Cout, Tout, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().vnb_codec_conv1d(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(alpha), _lib.ptr(resid),
+                                               _lib.ptr(y), B, Cin, Tin, Cout, Tout, K, stride, dil, pad, 1, 0, Tout,
+                                               1 if tanh else 0, _lib.stream_ptr(x.device)))
+        return y
+
+    def _convt(self, x, idx, s, alpha):
+        B, Cin, Tin = x.shape
+        wp = self._packed()[f"convt{idx}"]  # (s, cout, cin, 2)
+        b = self.params.get(f"decoder.block.{idx}.conv_t1.bias")
+        Cout = wp.shape[1]
+        pad = math.ceil(s / 2)
+        Tout = (Tin - 1) * s - 2 * pad + 2 * s
+        y = torch.empty(B, Cout, Tout, device=x.device, dtype=torch.float32)
+        for r in range(s):
+            _lib.check(_lib.lib().vnb_codec_conv1d(_lib.ptr(x), _lib.ptr(wp[r]), _lib.ptr(b), _lib.ptr(alpha), None,
+                                                   _lib.ptr(y), B, Cin, Tin, Cout, Tout, 2, 1, -1, 0, s, r - pad, Tin + 1,
+                                                   0, _lib.stream_ptr(x.device)))
+        return y
+
+    def _res_unit(self, x, name, dil):
+        P = self.params.get
+        y = self._conv(x, name + ".conv1", 7, dil=dil, pad=3 * dil, alpha=P(name + ".snake1.alpha"))
+        return self._conv(y, name + ".conv2", 1, alpha=P(name + ".snake2.alpha"), resid=x, out=x)  # in place: x += ...
+
+    # ---- public surface ------------------------------------------------------------------------
+    def preprocess(self, audio_data, sample_rate=None):
+        """Right-pad to a multiple of hop_length; returns (padded, original_length) (interface.py:215)."""
+        if sample_rate is not None:
+            assert sample_rate == self.sample_rate, f"expected {self.sample_rate} Hz, got {sample_rate}"
+        length = audio_data.shape[-1]
+        right = math.ceil(length / self.hop_length) * self.hop_length - length
+        return torch.nn.functional.pad(audio_data, (0, right)), length
+
+    @torch.no_grad()
+    def encode(self, audio_data: torch.Tensor, sample_rate: int = None, n_quantizers: int = None):
+        """(B, 1, N) -> dict(z, codes (B, n_codebooks, N/hop) int64, latents)  (interface.py:223)."""
+        self._packed()
+        x = audio_data.to(self.device, torch.float32).contiguous()
+        P = self.params.get
+        with torch.cuda.device(self.device):
+            h = self._conv(x, "encoder.conv1", 7, pad=3)
+            for i, s in enumerate(self.encoder_rates):
+                p = f"encoder.block.{i}"
+                for r, dil in enumerate((1, 3, 9)):
+                    h = self._res_unit(h, f"{p}.res_unit{r + 1}", dil)
+                h = self._conv(h, p + ".conv1", 2 * s, stride=s, pad=math.ceil(s / 2), alpha=P(p + ".snake1.alpha"))
+            z = self._conv(h, "encoder.conv2", 3, pad=1, alpha=P("encoder.snake1.alpha"))
+            zq, codes, lat = self.quantizer(z)
+        return {"z": zq, "codes": codes, "latents": lat, "length": audio_data.shape[-1]}
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, length: int = None):
+        """(B, latent_dim, T) -> dict(audio (B, 1, T*hop))  (transformer.py:671-675)."""
+        self._packed()
+        P = self.params.get
+        z = z.to(self.device, torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            h = self._conv(z, "decoder.conv1", 7, pad=3)
+            for i, s in enumerate(self.decoder_rates):
+                p = f"decoder.block.{i}"
+                h = self._convt(h, i, s, P(p + ".snake1.alpha"))
+                for r, dil in enumerate((1, 3, 9)):
+                    h = self._res_unit(h, f"{p}.res_unit{r + 1}", dil)
+            audio = self._conv(h, "decoder.conv2", 7, pad=3, alpha=P("decoder.snake1.alpha"), tanh=True)
+        return {"audio": audio if length is None else audio[..., :length]}
+
+    def forward(self, audio_data, sample_rate=None):
+        enc = self.encode(audio_data, sample_rate)
+        return {**enc, **self.decode(enc["z"], audio_data.shape[-1])}

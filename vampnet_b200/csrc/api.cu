@@ -267,6 +267,9 @@ using namespace vnb;
 extern "C" {
 
 int32_t vnb_abi_version(void) { return VNB_ABI_VERSION; }
+int32_t vnb_set_error_cuda(const char* what, int32_t cuda_error) {
+  return fail("%s failed: %s", what, cudaGetErrorString(static_cast<cudaError_t>(cuda_error)));
+}
 const char* vnb_last_error(void) { return g_err.c_str(); }
 
 int32_t vnb_model_create(const vnb_config* cfg, const vnb_weights* w, vnb_model** out) {

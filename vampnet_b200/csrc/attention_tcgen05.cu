@@ -9,11 +9,13 @@
 // (2*sat+1)-entry table per head held in shared memory.
 //
 // One CTA = one (batch, head, 128-query tile); key/value blocks of 64:
-//   warp 0      TMA producer (Q once; K_j and V^T_j through a 2-stage ring); owns the TMEM allocation
-//   warp 1      MMA issuer   S = Q.K_j^T (tcgen05.mma M128 N64 K16 x4) ; O += P_j.V_j (same shape)
+//   warp 0      TMA producer (Q once; K_j and V^T_j through a 4-stage ring); owns the TMEM allocation
+//   warp 1      MMA issuer   S[j&1] = Q.K_j^T (tcgen05.mma M128 N64 K16 x4), issued one block AHEAD of the
+//                            softmax into a double-buffered TMEM score tile ; O += P_j.V_j (same shape)
 //   warps 2..5  softmax      one thread per query row: tcgen05.ld S -> scale+bias -> running max ->
 //                            exp2 -> bf16 P into 128B-swizzled smem (A operand of P.V) ; O stays in TMEM
-//                            and is rescaled in place only when a row's running max grows.
+//                            and is rescaled in place only when a row's reference max grows by > 2^8
+//                            (lazy rescale: P may exceed 1 by that factor, harmless in bf16/fp32).
 // Roofline: tensor-bound in FLOPs (4*T^2*64 per (b,h)), but at d_head = 64 the per-block TMEM read
 // (128x64 fp32) and MUFU.EX2 cost as much as the two MMAs; see DESIGN.md.
 #include "common.cuh"
@@ -22,15 +24,17 @@
 namespace vnb {
 
 constexpr int AQ = 128, AK = 64, DH = 64;
+constexpr int KV_STAGES = 4;
 constexpr int Q_BYTES = AQ * DH * 2;   // 16 KiB
 constexpr int K_BYTES = AK * DH * 2;   // 8 KiB
 constexpr int V_BYTES = DH * AK * 2;   // 8 KiB
 constexpr int P_BYTES = AQ * AK * 2;   // 16 KiB
 constexpr int ATT_MAX_SAT = 128;
-constexpr int ATT_SMEM_TILES = Q_BYTES + 2 * K_BYTES + 2 * V_BYTES + P_BYTES;  // 64 KiB
-constexpr int ATT_SMEM = ATT_SMEM_TILES + 1024 /*align*/ + (2 * ATT_MAX_SAT + 1) * 4 + 128 /*barriers*/;
+constexpr int ATT_SMEM_TILES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES;  // 96 KiB
+constexpr int ATT_SMEM = ATT_SMEM_TILES + 1024 /*align*/ + (2 * ATT_MAX_SAT + 2) * 4 + 256 /*barriers*/;
 constexpr int ATT_THREADS = 192;
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 domain: O is rescaled only when a row max grows by > 2^8
 
 struct AttnArgs {
   __nv_bfloat16* out;
@@ -38,24 +42,48 @@ struct AttnArgs {
   int sat, B, T, H, d;
 };
 
+// One 64-key block of one query row: turn raw scores (TMEM) into exp2-domain logits, return the row max.
+template <bool TAIL, bool LOOKUP>
+__device__ __forceinline__ float scores_to_logits(uint32_t (&sr)[64], float c, float bconst, const float* sBias,
+                                                  int base, int sat2, int valid) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    float t;
+    if constexpr (LOOKUP) {
+      int idx = base + i;
+      idx = idx < 0 ? 0 : (idx > sat2 ? sat2 : idx);
+      t = fmaf(__uint_as_float(sr[i]), c, sBias[idx]);
+    } else {
+      t = fmaf(__uint_as_float(sr[i]), c, bconst);
+    }
+    if constexpr (TAIL) {
+      if (i >= valid) t = -INFINITY;
+    }
+    sr[i] = __float_as_uint(t);
+    mx = fmaxf(mx, t);
+  }
+  return mx;
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmVT, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;          // 2 stages
-  uint8_t* sV = sK + 2 * K_BYTES;      // 2 stages
-  uint8_t* sP = sV + 2 * V_BYTES;
+  uint8_t* sK = sQ + Q_BYTES;                  // KV_STAGES stages
+  uint8_t* sV = sK + KV_STAGES * K_BYTES;      // KV_STAGES stages
+  uint8_t* sP = sV + KV_STAGES * V_BYTES;
   float* sBias = reinterpret_cast<float*>(sP + P_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * ATT_MAX_SAT + 2);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;                    // [KV_STAGES]
+  uint64_t* kv_empty = kv_full + KV_STAGES;        // [KV_STAGES]
+  uint64_t* s_full = kv_empty + KV_STAGES;         // [2]
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,11 +94,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     mbar_fence_init();
@@ -82,7 +111,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tma_prefetch_desc(&tmVT);
     }
     __syncwarp();
-    tmem_alloc<128>(tmem_slot);
+    tmem_alloc<256>(tmem_slot);
   }
   // bias table for this head, pre-multiplied by log2(e)
   for (int i = threadIdx.x; i < 2 * a.sat + 1; i += ATT_THREADS) sBias[i] = a.rel[i * a.H + h] * LOG2E;
@@ -90,8 +119,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // columns [0, 64)
-  const uint32_t tmem_O = tmem_base + 64;   // columns [64, 128)
+  const uint32_t tmem_S = tmem_base;         // two score buffers: columns [0,64) and [64,128)
+  const uint32_t tmem_O = tmem_base + 128;   // columns [128, 192)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -99,8 +128,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_expect_tx(q_full, Q_BYTES);
       tma_load_3d(sQ, &tmQ, q_full, h * DH, q0, b);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
         mbar_wait(&kv_empty[st], ph ^ 1, 500 + st);
         mbar_expect_tx(&kv_full[st], K_BYTES + V_BYTES);
         tma_load_3d(sK + st * K_BYTES, &tmK, &kv_full[st], a.d + h * DH, j * AK, b);
@@ -112,16 +141,23 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(AQ, AK);  // M=128, N=64 for both products
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      mbar_wait(q_full, 0, 510);
-      mbar_wait(&kv_full[0], 0, 511);
-      tc_fence_after();
+      auto issue_qk = [&](int j) {  // S[j&1] = Q . K_j^T, one block ahead of the softmax
+        const int st = j % KV_STAGES;
+        mbar_wait(&kv_full[st], (j / KV_STAGES) & 1, 510 + st);
+        tc_fence_after();
+        const uint32_t aK = smem_u32(sK + st * K_BYTES);
+        const uint32_t dS = tmem_S + (j & 1) * 64;
 #pragma unroll
-      for (int k = 0; k < DH / 16; ++k)
-        umma_bf16(tmem_S, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(smem_u32(sK) + k * 32), idesc, k != 0);
-      umma_commit(s_full);
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16(dS, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc, k != 0);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0, 509);
+      issue_qk(0);
+      if (nblk > 1) issue_qk(1);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1, 520);
+        const int st = j % KV_STAGES;
+        mbar_wait(p_full, j & 1, 520);  // P_j is in smem, S[j&1] has been consumed
         tc_fence_after();
         const uint32_t aV = smem_u32(sV + st * V_BYTES);
 #pragma unroll
@@ -129,16 +165,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           umma_bf16(tmem_O, umma_desc_sw128(aP + k * 32), umma_desc_sw128(aV + k * 32), idesc, (j | k) != 0);
         umma_commit(&kv_empty[st]);
         umma_commit(o_full);
-        if (j + 1 < nblk) {
-          const int st2 = (j + 1) & 1;
-          mbar_wait(&kv_full[st2], ((j + 1) >> 1) & 1, 530 + st2);
-          tc_fence_after();
-          const uint32_t aK = smem_u32(sK + st2 * K_BYTES);
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            umma_bf16(tmem_S, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc, k != 0);
-          umma_commit(s_full);
-        }
+        if (j + 2 < nblk) issue_qk(j + 2);
       }
     }
   } else {
@@ -155,49 +182,43 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
     for (int j = 0; j < nblk; ++j) {
       const int k0 = j * AK;
-      mbar_wait(s_full, j & 1, 540);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1, 540 + (j & 1));
       tc_fence_after();
       uint32_t sr[64];
       {
         uint32_t t0[32], t1[32];
-        tmem_ld_x32(tmem_S + lane_off, t0);
-        tmem_ld_x32(tmem_S + lane_off + 32, t1);
+        const uint32_t src = tmem_S + (j & 1) * 64 + lane_off;
+        tmem_ld_x32(src, t0);
+        tmem_ld_x32(src + 32, t1);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) { sr[i] = t0[i]; sr[32 + i] = t1[i]; }
       }
       // scale + bias (+ mask of keys beyond T), all in the log2 domain
       const int rel_lo = k0 - (q0 + AQ - 1), rel_hi = k0 + AK - 1 - q0;
-      float mx = -INFINITY;
-      if (rel_lo >= sat || rel_hi <= -sat) {
-        const float bconst = sBias[rel_lo >= sat ? 2 * sat : 0];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          float t = fmaf(__uint_as_float(sr[i]), c, bconst);
-          if (k0 + i >= a.T) t = -INFINITY;
-          sr[i] = __float_as_uint(t);
-          mx = fmaxf(mx, t);
-        }
+      const bool is_const = (rel_lo >= sat) || (rel_hi <= -sat);
+      const bool tail = k0 + AK > a.T;
+      const float bconst = sBias[rel_lo >= sat ? 2 * sat : 0];
+      const int base = k0 - q + sat;
+      const int valid = a.T - k0;
+      float mx;
+      if (is_const) {
+        mx = tail ? scores_to_logits<true, false>(sr, c, bconst, sBias, base, 2 * sat, valid)
+                  : scores_to_logits<false, false>(sr, c, bconst, sBias, base, 2 * sat, valid);
       } else {
-        const int base = k0 - q + sat;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          int idx = base + i;
-          idx = idx < 0 ? 0 : (idx > 2 * sat ? 2 * sat : idx);
-          float t = fmaf(__uint_as_float(sr[i]), c, sBias[idx]);
-          if (k0 + i >= a.T) t = -INFINITY;
-          sr[i] = __float_as_uint(t);
-          mx = fmaxf(mx, t);
-        }
+        mx = tail ? scores_to_logits<true, true>(sr, c, bconst, sBias, base, 2 * sat, valid)
+                  : scores_to_logits<false, true>(sr, c, bconst, sBias, base, 2 * sat, valid);
       }
-      const float m_new = fmaxf(m_ref, mx);
-      if (j > 0) {
-        // P.V of the previous block must have retired: P buffer is free and O is stable.
+      if (j == 0) {
+        m_ref = mx;
+      } else {
+        // P.V of the previous block must have retired: the P buffer is free and O is stable.
         mbar_wait(o_full, (j - 1) & 1, 550);
         tc_fence_after();
-        const bool grow = m_new > m_ref;
+        const bool grow = mx > m_ref + RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, grow)) {
-          const float alpha = fast_exp2(m_ref - m_new);  // 1 for rows whose max did not grow
+          const float m_new = grow ? mx : m_ref;
+          const float alpha = fast_exp2(m_ref - m_new);  // exactly 1 for rows that keep their reference
           uint32_t o[32];
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -209,9 +230,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           }
           tmem_wait_st();
           l *= alpha;
+          m_ref = m_new;
         }
       }
-      m_ref = m_new;
       float psum = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
@@ -260,7 +281,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<128>(tmem_base);
+  if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
 cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st) {

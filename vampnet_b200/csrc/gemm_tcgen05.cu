@@ -25,7 +25,8 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_STG_BYTES = 4 * 32 * 36 * 4;  // epilogue staging: 4 warps x (32 rows x 36 floats)
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + GEMM_STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 256;
 
 struct GemmArgs {
@@ -46,84 +47,67 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + t);
 }
 
+// ---- epilogue ---------------------------------------------------------------------------------
+// tcgen05.ld hands every lane one accumulator ROW (32 consecutive columns).  Writing that straight to
+// global memory makes each warp instruction touch 32 different 128-byte lines.  Instead each warp
+// transposes its 32x32 fp32 chunk through a padded shared-memory tile (row pitch 36 floats: the
+// 16-byte stores and loads below are bank-conflict free) so that a warp instruction covers whole
+// rows: 128 contiguous bytes per 8 lanes for fp32 outputs, 64 for bf16.
+constexpr int STG_PITCH = 36;
+constexpr int STG_FLOATS_PER_WARP = 32 * STG_PITCH;
+
+__device__ __forceinline__ void stage_rows(float* stg, int lane, const float (&v)[32]) {
+  float4* dst = reinterpret_cast<float4*>(stg + lane * STG_PITCH);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  __syncwarp();
+}
+
+// fp32 destinations: lane -> (row = it*4 + lane/8, 4 columns at (lane%8)*4)
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int row, int col0, bool row_ok,
-                                               const uint32_t (&v)[32], const uint32_t (&v2)[32], int b_idx,
-                                               int t_idx) {
-  if (!row_ok) return;
-  if constexpr (EPI == VNB_EPI_BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<size_t>(row) * g.N + col0;
-    uint4* o4 = reinterpret_cast<uint4*>(o);
+__device__ __forceinline__ void drain_f32(const GemmArgs& g, const float* stg, int lane, int row_base, int col0) {
+  const int c4 = (lane & 7) * 4;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (EPI == VNB_EPI_BIAS_F32) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + c4));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 w;
-      w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
-      w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-      w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-      w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
-      o4[i] = w;
-    }
-  } else if constexpr (EPI == VNB_EPI_QKV) {
-    if (col0 < g.d2) {  // q | k : row-major (M, 2d)
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<size_t>(row) * g.d2 + col0;
-      uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 w;
-        w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
-        w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-        w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-        w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
-        o4[i] = w;
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    const int row = row_base + r;
+    if (row < g.M) {
+      float4 a = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c4);
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<size_t>(row) * g.N + col0 + c4);
+      if constexpr (EPI == VNB_EPI_RESID) {
+        const float4 x = *o;
+        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+      } else {
+        a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
       }
-    } else {  // v : transposed (B, d, Tpad) so that attention's P.V B-operand is K-major over keys
-      const int d = g.N - g.d2;
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out2) +
-                         (static_cast<size_t>(b_idx) * d + (col0 - g.d2)) * g.Tpad + t_idx;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) o[static_cast<size_t>(j) * g.Tpad] = __float2bfloat16_rn(__uint_as_float(v[j]));
-    }
-  } else if constexpr (EPI == VNB_EPI_RESID) {
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<size_t>(row) * g.N + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 x = o4[i];
-      x.x += __uint_as_float(v[4 * i + 0]);
-      x.y += __uint_as_float(v[4 * i + 1]);
-      x.z += __uint_as_float(v[4 * i + 2]);
-      x.w += __uint_as_float(v[4 * i + 3]);
-      o4[i] = x;
-    }
-  } else if constexpr (EPI == VNB_EPI_GEGLU) {
-    // v = value columns, v2 = gate columns of the same output features (weights interleaved at pack time)
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + static_cast<size_t>(row) * (g.N / 2) + col0;
-    uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float r[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = __uint_as_float(v[8 * i + j]) * gelu_tanh(__uint_as_float(v2[8 * i + j]));
-      uint4 w;
-      w.x = pack_bf16x2(r[0], r[1]);
-      w.y = pack_bf16x2(r[2], r[3]);
-      w.z = pack_bf16x2(r[4], r[5]);
-      w.w = pack_bf16x2(r[6], r[7]);
-      o4[i] = w;
-    }
-  } else {  // VNB_EPI_BIAS_F32
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<size_t>(row) * g.N + col0);
-    const float4* b4 = reinterpret_cast<const float4*>(g.bias + col0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(b4 + i);
-      float4 x;
-      x.x = __uint_as_float(v[4 * i + 0]) + b.x;
-      x.y = __uint_as_float(v[4 * i + 1]) + b.y;
-      x.z = __uint_as_float(v[4 * i + 2]) + b.z;
-      x.w = __uint_as_float(v[4 * i + 3]) + b.w;
-      o4[i] = x;
+      *o = a;
     }
   }
+  __syncwarp();
+}
+
+// bf16 destinations: lane -> (row = it*8 + lane/4, 8 columns at (lane%4)*8); `pitch` = output row pitch
+__device__ __forceinline__ void drain_bf16(__nv_bfloat16* out, int pitch, int M, const float* stg, int lane,
+                                           int row_base, int col0) {
+  const int c8 = (lane & 3) * 8;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane >> 2);
+    const int row = row_base + r;
+    if (row < M) {
+      const float4 a = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c8);
+      const float4 b = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c8 + 4);
+      uint4 w;
+      w.x = pack_bf16x2(a.x, a.y);
+      w.y = pack_bf16x2(a.z, a.w);
+      w.z = pack_bf16x2(b.x, b.y);
+      w.w = pack_bf16x2(b.z, b.w);
+      *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * pitch + col0 + c8) = w;
+    }
+  }
+  __syncwarp();
 }
 
 template <int EPI>
@@ -133,7 +117,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms are 1024 B: align the tile ring to 1024.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + GEMM_STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
@@ -235,6 +220,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      float* stg = stg_all + quad * STG_FLOATS_PER_WARP;
+      const int row_base = m0 + quad * 32;
       if constexpr (EPI == VNB_EPI_GEGLU) {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -242,7 +229,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_x32(t_addr + c * 32, v);
           tmem_ld_x32(t_addr + 128 + c * 32, v2);
           tmem_wait_ld();
-          epilogue_chunk<EPI>(g, row, (n0 >> 1) + c * 32, row_ok, v, v2, b_idx, t_idx);
+          float r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]) * gelu_tanh(__uint_as_float(v2[j]));
+          stage_rows(stg, lane, r);
+          drain_bf16(reinterpret_cast<__nv_bfloat16*>(g.out), g.N / 2, g.M, stg, lane, row_base, (n0 >> 1) + c * 32);
         }
       } else {
 #pragma unroll 1
@@ -250,7 +241,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t v[32];
           tmem_ld_x32(t_addr + c * 32, v);
           tmem_wait_ld();
-          epilogue_chunk<EPI>(g, row, n0 + c * 32, row_ok, v, v, b_idx, t_idx);
+          const int col0 = n0 + c * 32;
+          if constexpr (EPI == VNB_EPI_QKV) {
+            if (col0 >= g.d2) {
+              // v : transposed (B, d, Tpad) so that attention's P.V B-operand is K-major over keys.
+              // lane == row == consecutive t: each of the 32 stores is one contiguous 64-byte segment.
+              if (row_ok) {
+                const int d = g.N - g.d2;
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out2) +
+                                   (static_cast<size_t>(b_idx) * d + (col0 - g.d2)) * g.Tpad + t_idx;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  o[static_cast<size_t>(j) * g.Tpad] = __float2bfloat16_rn(__uint_as_float(v[j]));
+              }
+              continue;
+            }
+          }
+          float r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+          stage_rows(stg, lane, r);
+          if constexpr (EPI == VNB_EPI_BF16) {
+            drain_bf16(reinterpret_cast<__nv_bfloat16*>(g.out), g.N, g.M, stg, lane, row_base, col0);
+          } else if constexpr (EPI == VNB_EPI_QKV) {
+            drain_bf16(reinterpret_cast<__nv_bfloat16*>(g.out), g.d2, g.M, stg, lane, row_base, col0);
+          } else {
+            drain_f32<EPI>(g, stg, lane, row_base, col0);
+          }
         }
       }
       tc_fence_before();

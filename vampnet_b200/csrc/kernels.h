@@ -16,6 +16,10 @@ bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t col
 bool make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
                   uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols);
 const char* tmap_error();
+}  // namespace vnb
+// sets the thread-local error string from a CUDA error code; returns 1
+extern "C" int32_t vnb_set_error_cuda(const char* what, int32_t cuda_error);
+namespace vnb {
 
 // ---- GEMM ----
 struct GemmPlan {
