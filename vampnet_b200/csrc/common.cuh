@@ -45,22 +45,33 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint
+// expires, instead of returning immediately -- polling threads stop stealing issue slots from the math warps.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: traps with a message when the barrier never completes.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: traps with a message when the barrier has not completed after VNB_WAIT_TIMEOUT_NS.
+#ifndef VNB_WAIT_TIMEOUT_NS
+#define VNB_WAIT_TIMEOUT_NS 4000000000ull
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > VNB_SPIN_LIMIT) {
+    if (global_timer_ns() - t0 > VNB_WAIT_TIMEOUT_NS) {
       printf("[vnb] mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, parity);
       __trap();
