@@ -212,6 +212,8 @@ def main():
         run_attention(2, 575, 4)
         run_attention(8, 768, 20, timing=True)
         run_attention(2, 3072, 20, timing=True)
+    elif stage == "attention_b32":
+        run_attention(32, 768, 20, timing=True)
     else:
         raise SystemExit("unknown stage")
     print("=== done", flush=True)

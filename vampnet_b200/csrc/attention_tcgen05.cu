@@ -9,10 +9,11 @@
 // (2*sat+1)-entry table per head held in shared memory.
 //
 // One CTA = one (batch, head, 128-query tile); key/value blocks of 64:
-//   warp 0      TMA producer (Q once; K_j and V^T_j through a 4-stage ring); owns the TMEM allocation
+//   warp 0      TMA producer (Q once; K_j and V^T_j through a 3-stage ring); owns the TMEM allocation
 //   warp 1      MMA issuer   S[j&1] = Q.K_j^T (tcgen05.mma M128 N64 K16 x4), issued one block AHEAD of the
-//                            softmax into a double-buffered TMEM score tile ; O += P_j.V_j (same shape)
-//   warps 2..5  softmax      one thread per query row: tcgen05.ld S -> scale+bias -> running max ->
+//                            softmax into a double-buffered TMEM score tile ; O += P_j.V_j (same shape) from a
+//                            double-buffered P tile, so softmax(j+1) never waits for P.V(j)
+//   warps 2..9  softmax      two threads per query row (32 keys each): tcgen05.ld S -> scale+bias -> row max ->
 //                            exp2 -> bf16 P into 128B-swizzled smem (A operand of P.V) ; O stays in TMEM
 //                            and is rescaled in place only when a row's reference max grows by > 2^8
 //                            (lazy rescale: P may exceed 1 by that factor, harmless in bf16/fp32).
@@ -24,15 +25,16 @@
 namespace vnb {
 
 constexpr int AQ = 128, AK = 64, DH = 64;
-constexpr int KV_STAGES = 4;
+constexpr int KV_STAGES = 3;
 constexpr int Q_BYTES = AQ * DH * 2;   // 16 KiB
 constexpr int K_BYTES = AK * DH * 2;   // 8 KiB
 constexpr int V_BYTES = DH * AK * 2;   // 8 KiB
 constexpr int P_BYTES = AQ * AK * 2;   // 16 KiB
 constexpr int ATT_MAX_SAT = 128;
-constexpr int ATT_SMEM_TILES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + P_BYTES;  // 96 KiB
-constexpr int ATT_SMEM = ATT_SMEM_TILES + 1024 /*align*/ + (2 * ATT_MAX_SAT + 2) * 4 + 256 /*barriers*/;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_SMEM_TILES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES;  // 96 KiB (P double buffered)
+constexpr int ATT_SMEM = ATT_SMEM_TILES + 1024 /*align*/ + (2 * ATT_MAX_SAT + 2) * 4 + 2 * 2 * AQ * 4 /*row-max exchange*/ +
+                         256 /*barriers*/;
+constexpr int ATT_THREADS = 320;  // producer + MMA + 8 softmax warps (two threads per query row)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 domain: O is rescaled only when a row max grows by > 2^8
 
@@ -42,28 +44,39 @@ struct AttnArgs {
   int sat, B, T, H, d;
 };
 
-// One 64-key block of one query row: turn raw scores (TMEM) into exp2-domain logits, return the row max.
+// Half a 64-key block (32 keys) of one query row: turn raw scores (TMEM) into exp2-domain logits, return the
+// max over these 32.  Scale+bias runs as packed FFMA2 (two keys per issue slot).
 template <bool TAIL, bool LOOKUP>
-__device__ __forceinline__ float scores_to_logits(uint32_t (&sr)[64], float c, float bconst, const float* sBias,
+__device__ __forceinline__ float scores_to_logits(uint32_t (&sr)[32], float c, float bconst, const float* sBias,
                                                   int base, int sat2, int valid) {
   float mx = -INFINITY;
+  const uint64_t c2 = pack2(c, c);
+  const uint64_t b2c = pack2(bconst, bconst);
 #pragma unroll
-  for (int i = 0; i < 64; ++i) {
-    float t;
+  for (int i = 0; i < 32; i += 2) {
+    uint64_t b2 = b2c;
     if constexpr (LOOKUP) {
-      int idx = base + i;
-      idx = idx < 0 ? 0 : (idx > sat2 ? sat2 : idx);
-      t = fmaf(__uint_as_float(sr[i]), c, sBias[idx]);
-    } else {
-      t = fmaf(__uint_as_float(sr[i]), c, bconst);
+      int i0 = base + i, i1 = base + i + 1;
+      i0 = i0 < 0 ? 0 : (i0 > sat2 ? sat2 : i0);
+      i1 = i1 < 0 ? 0 : (i1 > sat2 ? sat2 : i1);
+      b2 = pack2(sBias[i0], sBias[i1]);
     }
+    const uint64_t t2 = ffma2(pack2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), c2, b2);
+    float t0, t1;
+    unpack2(t2, t0, t1);
     if constexpr (TAIL) {
-      if (i >= valid) t = -INFINITY;
+      if (i >= valid) t0 = -INFINITY;
+      if (i + 1 >= valid) t1 = -INFINITY;
     }
-    sr[i] = __float_as_uint(t);
-    mx = fmaxf(mx, t);
+    sr[i] = __float_as_uint(t0);
+    sr[i + 1] = __float_as_uint(t1);
+    mx = fmaxf(mx, fmaxf(t0, t1));
   }
   return mx;
+}
+
+__device__ __forceinline__ void pair_barrier(int id) {  // the two warps that share a TMEM lane quadrant
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -75,15 +88,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* sK = sQ + Q_BYTES;                  // KV_STAGES stages
   uint8_t* sV = sK + KV_STAGES * K_BYTES;      // KV_STAGES stages
   uint8_t* sP = sV + KV_STAGES * V_BYTES;
-  float* sBias = reinterpret_cast<float*>(sP + P_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * ATT_MAX_SAT + 2);
+  float* sBias = reinterpret_cast<float*>(sP + 2 * P_BYTES);
+  float* sMx = sBias + 2 * ATT_MAX_SAT + 2;  // [2 buffers][2 halves][128 rows] row-max / row-sum exchange
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMx + 2 * 2 * AQ);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;                    // [KV_STAGES]
   uint64_t* kv_empty = kv_full + KV_STAGES;        // [KV_STAGES]
   uint64_t* s_full = kv_empty + KV_STAGES;         // [2]
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* p_full = s_full + 2;                   // [2] P buffer written (per buffer: a lagging MMA thread can
+                                                   //     never fall two phases behind on the same barrier)
+  uint64_t* p_free = p_full + 2;                   // [2] P buffer consumed by its P.V (also: O updated)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,8 +115,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    mbar_init(&p_full[0], 256);
+    mbar_init(&p_full[1], 256);
+    mbar_init(&p_free[0], 1);
+    mbar_init(&p_free[1], 1);
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -157,47 +174,42 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (nblk > 1) issue_qk(1);
       for (int j = 0; j < nblk; ++j) {
         const int st = j % KV_STAGES;
-        mbar_wait(p_full, j & 1, 520);  // P_j is in smem, S[j&1] has been consumed
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1, 520);  // P_j is in smem, S[j&1] has been consumed
         tc_fence_after();
         const uint32_t aV = smem_u32(sV + st * V_BYTES);
+        const uint32_t aPj = aP + (j & 1) * P_BYTES;
 #pragma unroll
         for (int k = 0; k < AK / 16; ++k)
-          umma_bf16(tmem_O, umma_desc_sw128(aP + k * 32), umma_desc_sw128(aV + k * 32), idesc, (j | k) != 0);
+          umma_bf16(tmem_O, umma_desc_sw128(aPj + k * 32), umma_desc_sw128(aV + k * 32), idesc, (j | k) != 0);
         umma_commit(&kv_empty[st]);
-        umma_commit(o_full);
+        umma_commit(&p_free[j & 1]);
         if (j + 2 < nblk) issue_qk(j + 2);
       }
     }
   } else {
-    // ===================== softmax warps (one thread per query row) =====================
-    const int quad = warp & 3;
+    // ===================== softmax warps: two threads per query row (32 keys of each block each) ==========
+    const int quad = warp & 3;                 // TMEM lane quadrant of this warp
+    const int half = (warp - 2) >> 2;          // 0: keys [0,32) of the block, 1: keys [32,64)
     const int row = quad * 32 + lane;
     const int q = q0 + row;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const float c = 0.125f * LOG2E;  // 1/sqrt(64) folded with log2(e)
     const int sat = a.sat;
     float m_ref = -INFINITY, l = 0.f;
-    uint8_t* prow = sP + row * 128;
     const int sw = row & 7;
 
     for (int j = 0; j < nblk; ++j) {
-      const int k0 = j * AK;
+      const int k0 = j * AK + half * 32;
+      uint8_t* prow = sP + (j & 1) * P_BYTES + row * 128;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1, 540 + (j & 1));
       tc_fence_after();
-      uint32_t sr[64];
-      {
-        uint32_t t0[32], t1[32];
-        const uint32_t src = tmem_S + (j & 1) * 64 + lane_off;
-        tmem_ld_x32(src, t0);
-        tmem_ld_x32(src + 32, t1);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { sr[i] = t0[i]; sr[32 + i] = t1[i]; }
-      }
+      uint32_t sr[32];
+      tmem_ld_x32(tmem_S + (j & 1) * 64 + half * 32 + lane_off, sr);
+      tmem_wait_ld();
       // scale + bias (+ mask of keys beyond T), all in the log2 domain
-      const int rel_lo = k0 - (q0 + AQ - 1), rel_hi = k0 + AK - 1 - q0;
+      const int rel_lo = k0 - (q0 + AQ - 1), rel_hi = k0 + 31 - q0;
       const bool is_const = (rel_lo >= sat) || (rel_hi <= -sat);
-      const bool tail = k0 + AK > a.T;
+      const bool tail = k0 + 32 > a.T;
       const float bconst = sBias[rel_lo >= sat ? 2 * sat : 0];
       const int base = k0 - q + sat;
       const int valid = a.T - k0;
@@ -209,63 +221,74 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         mx = tail ? scores_to_logits<true, true>(sr, c, bconst, sBias, base, 2 * sat, valid)
                   : scores_to_logits<false, true>(sr, c, bconst, sBias, base, 2 * sat, valid);
       }
+      // row max over both halves (partner = same lane of warp +-4)
+      float* ex = sMx + (j & 1) * 2 * AQ;
+      ex[half * AQ + row] = mx;
+      pair_barrier(1 + quad);
+      mx = fmaxf(mx, ex[(half ^ 1) * AQ + row]);
       if (j == 0) {
         m_ref = mx;
       } else {
-        // P.V of the previous block must have retired: the P buffer is free and O is stable.
-        mbar_wait(o_full, (j - 1) & 1, 550);
-        tc_fence_after();
         const bool grow = mx > m_ref + RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, grow)) {
+          // rare: O must be stable, i.e. the P.V of the previous block has retired
+          mbar_wait(&p_free[(j - 1) & 1], ((j - 1) >> 1) & 1, 550);
+          tc_fence_after();
           const float m_new = grow ? mx : m_ref;
           const float alpha = fast_exp2(m_ref - m_new);  // exactly 1 for rows that keep their reference
           uint32_t o[32];
+          tmem_ld_x32(tmem_O + lane_off + half * 32, o);  // each half rescales its own 32 output columns
+          tmem_wait_ld();
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            tmem_ld_x32(tmem_O + lane_off + hh * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x32(tmem_O + lane_off + hh * 32, o);
-          }
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x32(tmem_O + lane_off + half * 32, o);
           tmem_wait_st();
           l *= alpha;
           m_ref = m_new;
         }
       }
-      float psum = 0.f;
+      // this block's P buffer was last read by the P.V of block j-2
+      if (j >= 2) mbar_wait(&p_free[j & 1], ((j - 2) >> 1) & 1, 555);
+      uint64_t psum2 = pack2(0.f, 0.f);
+      const uint64_t negm2 = pack2(-m_ref, -m_ref);
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        float p[8];
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          p[i] = fast_exp2(__uint_as_float(sr[ch * 8 + i]) - m_ref);
-          psum += p[i];
+        for (int i = 0; i < 4; ++i) {
+          const uint64_t d2 = fadd2(pack2(__uint_as_float(sr[ch * 8 + 2 * i]), __uint_as_float(sr[ch * 8 + 2 * i + 1])), negm2);
+          float d0, d1;
+          unpack2(d2, d0, d1);
+          const float p0 = fast_exp2(d0), p1 = fast_exp2(d1);
+          psum2 = fadd2(psum2, pack2(p0, p1));
+          pk[i] = pack_bf16x2(p0, p1);
         }
-        uint4 w;
-        w.x = pack_bf16x2(p[0], p[1]);
-        w.y = pack_bf16x2(p[2], p[3]);
-        w.z = pack_bf16x2(p[4], p[5]);
-        w.w = pack_bf16x2(p[6], p[7]);
-        *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = w;
+        *reinterpret_cast<uint4*>(prow + (((half * 4 + ch) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      l += psum;
+      float ps0, ps1;
+      unpack2(psum2, ps0, ps1);
+      l += ps0 + ps1;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[j & 1]);
     }
-    // ---- finalize: O / l -> bf16 -> (B, T, d) at [b, q, h*64 ..]
-    mbar_wait(o_full, (nblk - 1) & 1, 560);
+    // ---- finalize: O / l -> bf16 -> (B, T, d) at [b, q, h*64 + half*32 ..]
+    {
+      float* ex = sMx + (nblk & 1) * 2 * AQ;
+      ex[half * AQ + row] = l;
+      pair_barrier(1 + quad);
+      l += ex[(half ^ 1) * AQ + row];
+    }
+    mbar_wait(&p_free[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1, 560);
     tc_fence_after();
     const float inv_l = 1.0f / l;
-    __nv_bfloat16* orow = a.out + (static_cast<size_t>(b) * a.T + q) * a.d + h * DH;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
+    __nv_bfloat16* orow = a.out + (static_cast<size_t>(b) * a.T + q) * a.d + h * DH + half * 32;
+    {
       uint32_t o[32];
-      tmem_ld_x32(tmem_O + lane_off + hh * 32, o);
+      tmem_ld_x32(tmem_O + lane_off + half * 32, o);
       tmem_wait_ld();
       if (q < a.T) {
-        uint4* o4 = reinterpret_cast<uint4*>(orow + hh * 32);
+        uint4* o4 = reinterpret_cast<uint4*>(orow);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 w;

@@ -63,27 +63,38 @@ __device__ __forceinline__ void stage_rows(float* stg, int lane, const float (&v
   __syncwarp();
 }
 
-// fp32 destinations: lane -> (row = it*4 + lane/8, 4 columns at (lane%8)*4)
+// fp32 destinations: lane -> (row = it*4 + lane/8, 4 columns at (lane%8)*4).
+// The addend (residual rows or bias) is fetched by prefetch_addend() BEFORE the accumulator chunk is pulled
+// out of TMEM, so the global-load latency overlaps the tcgen05.ld and the shared-memory transpose, and all
+// eight loads are in flight before the first store.
 template <int EPI>
-__device__ __forceinline__ void drain_f32(const GemmArgs& g, const float* stg, int lane, int row_base, int col0) {
+__device__ __forceinline__ void prefetch_addend(const GemmArgs& g, int lane, int row_base, int col0, float4 (&add)[8]) {
   const int c4 = (lane & 7) * 4;
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if constexpr (EPI == VNB_EPI_BIAS_F32) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + c4));
+  const int r0 = row_base + (lane >> 3);
+  if constexpr (EPI == VNB_EPI_RESID) {
+    const float* base = reinterpret_cast<const float*>(g.out) + static_cast<size_t>(r0) * g.N + col0 + c4;
+    const size_t step = static_cast<size_t>(4) * g.N;
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      add[it] = (r0 + it * 4 < g.M) ? __ldcg(reinterpret_cast<const float4*>(base + it * step))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + c4));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) add[it] = b4;
+  }
+}
+__device__ __forceinline__ void drain_f32(const GemmArgs& g, const float* stg, int lane, int row_base, int col0,
+                                          const float4 (&add)[8]) {
+  const int c4 = (lane & 7) * 4;
+  const int r0 = row_base + (lane >> 3);
+  float* const base = reinterpret_cast<float*>(g.out) + static_cast<size_t>(r0) * g.N + col0 + c4;
+  const size_t step = static_cast<size_t>(4) * g.N;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    const int row = row_base + r;
-    if (row < g.M) {
-      float4 a = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c4);
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + static_cast<size_t>(row) * g.N + col0 + c4);
-      if constexpr (EPI == VNB_EPI_RESID) {
-        const float4 x = *o;
-        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
-      } else {
-        a.x += bias4.x; a.y += bias4.y; a.z += bias4.z; a.w += bias4.w;
-      }
-      *o = a;
-    }
+    float4 a = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * STG_PITCH + c4);
+    a.x += add[it].x; a.y += add[it].y; a.z += add[it].z; a.w += add[it].w;
+    if (r0 + it * 4 < g.M) *reinterpret_cast<float4*>(base + it * step) = a;
   }
   __syncwarp();
 }
@@ -238,10 +249,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          float4 addend[8];
+          if constexpr (EPI == VNB_EPI_RESID || EPI == VNB_EPI_BIAS_F32) prefetch_addend<EPI>(g, lane, row_base, col0, addend);
           uint32_t v[32];
           tmem_ld_x32(t_addr + c * 32, v);
           tmem_wait_ld();
-          const int col0 = n0 + c * 32;
           if constexpr (EPI == VNB_EPI_QKV) {
             if (col0 >= g.d2) {
               // v : transposed (B, d, Tpad) so that attention's P.V B-operand is K-major over keys.
@@ -266,7 +279,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else if constexpr (EPI == VNB_EPI_QKV) {
             drain_bf16(reinterpret_cast<__nv_bfloat16*>(g.out), g.d2, g.M, stg, lane, row_base, col0);
           } else {
-            drain_f32<EPI>(g, stg, lane, row_base, col0);
+            drain_f32(g, stg, lane, row_base, col0, addend);
           }
         }
       }
