@@ -31,8 +31,10 @@ constexpr int K_BYTES = AK * DH * 2;   // 8 KiB
 constexpr int V_BYTES = DH * AK * 2;   // 8 KiB
 constexpr int P_BYTES = AQ * AK * 2;   // 16 KiB
 constexpr int ATT_MAX_SAT = 128;
+constexpr int ATT_PAD = 160;  // a lookup block spans 128 query rows + 32 keys: pad the table so indices never clamp
+constexpr int ATT_TAB = 2 * (ATT_MAX_SAT + ATT_PAD) + 2;
 constexpr int ATT_SMEM_TILES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES;  // 96 KiB (P double buffered)
-constexpr int ATT_SMEM = ATT_SMEM_TILES + 1024 /*align*/ + (2 * ATT_MAX_SAT + 2) * 4 + 2 * 2 * AQ * 4 /*row-max exchange*/ +
+constexpr int ATT_SMEM = ATT_SMEM_TILES + 1024 /*align*/ + ATT_TAB * 4 + 2 * 2 * AQ * 4 /*row-max exchange*/ +
                          256 /*barriers*/;
 constexpr int ATT_THREADS = 320;  // producer + MMA + 8 softmax warps (two threads per query row)
 constexpr float LOG2E = 1.4426950408889634f;
@@ -47,20 +49,15 @@ struct AttnArgs {
 // Half a 64-key block (32 keys) of one query row: turn raw scores (TMEM) into exp2-domain logits, return the
 // max over these 32.  Scale+bias runs as packed FFMA2 (two keys per issue slot).
 template <bool TAIL, bool LOOKUP>
-__device__ __forceinline__ float scores_to_logits(uint32_t (&sr)[32], float c, float bconst, const float* sBias,
-                                                  int base, int sat2, int valid) {
+__device__ __forceinline__ float scores_to_logits(uint32_t (&sr)[32], float c, float bconst, uint32_t bias_addr,
+                                                  int valid) {
   float mx = -INFINITY;
   const uint64_t c2 = pack2(c, c);
   const uint64_t b2c = pack2(bconst, bconst);
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
     uint64_t b2 = b2c;
-    if constexpr (LOOKUP) {
-      int i0 = base + i, i1 = base + i + 1;
-      i0 = i0 < 0 ? 0 : (i0 > sat2 ? sat2 : i0);
-      i1 = i1 < 0 ? 0 : (i1 > sat2 ? sat2 : i1);
-      b2 = pack2(sBias[i0], sBias[i1]);
-    }
+    if constexpr (LOOKUP) b2 = pack2(lds_f32(bias_addr + 4 * i), lds_f32(bias_addr + 4 * i + 4));
     const uint64_t t2 = ffma2(pack2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), c2, b2);
     float t0, t1;
     unpack2(t2, t0, t1);
@@ -89,7 +86,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* sV = sK + KV_STAGES * K_BYTES;      // KV_STAGES stages
   uint8_t* sP = sV + KV_STAGES * V_BYTES;
   float* sBias = reinterpret_cast<float*>(sP + 2 * P_BYTES);
-  float* sMx = sBias + 2 * ATT_MAX_SAT + 2;  // [2 buffers][2 halves][128 rows] row-max / row-sum exchange
+  float* sMx = sBias + ATT_TAB;  // [2 buffers][2 halves][128 rows] row-max / row-sum exchange
   uint64_t* bars = reinterpret_cast<uint64_t*>(sMx + 2 * 2 * AQ);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;                    // [KV_STAGES]
@@ -131,7 +128,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     tmem_alloc<256>(tmem_slot);
   }
   // bias table for this head, pre-multiplied by log2(e)
-  for (int i = threadIdx.x; i < 2 * a.sat + 1; i += ATT_THREADS) sBias[i] = a.rel[i * a.H + h] * LOG2E;
+  // entry [rel + sat + ATT_PAD] for rel in [-(sat+PAD), sat+PAD], saturated outside [-sat, sat]
+  for (int i = threadIdx.x; i < 2 * (a.sat + ATT_PAD) + 1; i += ATT_THREADS) {
+    int r = i - ATT_PAD;
+    r = r < 0 ? 0 : (r > 2 * a.sat ? 2 * a.sat : r);
+    sBias[i] = a.rel[r * a.H + h] * LOG2E;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -197,10 +199,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const int sat = a.sat;
     float m_ref = -INFINITY, l = 0.f;
     const int sw = row & 7;
+    const uint32_t sBias_addr = smem_u32(sBias), sMx_addr = smem_u32(sMx), sP_addr = smem_u32(sP);
+    const float bias_lo = sBias[0], bias_hi = sBias[2 * (sat + ATT_PAD)];
 
     for (int j = 0; j < nblk; ++j) {
       const int k0 = j * AK + half * 32;
-      uint8_t* prow = sP + (j & 1) * P_BYTES + row * 128;
+      const uint32_t prow = sP_addr + (j & 1) * P_BYTES + row * 128;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1, 540 + (j & 1));
       tc_fence_after();
       uint32_t sr[32];
@@ -210,22 +214,23 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const int rel_lo = k0 - (q0 + AQ - 1), rel_hi = k0 + 31 - q0;
       const bool is_const = (rel_lo >= sat) || (rel_hi <= -sat);
       const bool tail = k0 + 32 > a.T;
-      const float bconst = sBias[rel_lo >= sat ? 2 * sat : 0];
-      const int base = k0 - q + sat;
+      const float bconst = rel_lo >= sat ? bias_hi : bias_lo;
+      // lookup blocks satisfy |k0 - q0| < sat + 160, so rel + sat + ATT_PAD stays inside the padded table
+      const uint32_t bias_addr = sBias_addr + 4u * static_cast<uint32_t>(k0 - q + sat + ATT_PAD);
       const int valid = a.T - k0;
       float mx;
       if (is_const) {
-        mx = tail ? scores_to_logits<true, false>(sr, c, bconst, sBias, base, 2 * sat, valid)
-                  : scores_to_logits<false, false>(sr, c, bconst, sBias, base, 2 * sat, valid);
+        mx = tail ? scores_to_logits<true, false>(sr, c, bconst, bias_addr, valid)
+                  : scores_to_logits<false, false>(sr, c, bconst, bias_addr, valid);
       } else {
-        mx = tail ? scores_to_logits<true, true>(sr, c, bconst, sBias, base, 2 * sat, valid)
-                  : scores_to_logits<false, true>(sr, c, bconst, sBias, base, 2 * sat, valid);
+        mx = tail ? scores_to_logits<true, true>(sr, c, bconst, bias_addr, valid)
+                  : scores_to_logits<false, true>(sr, c, bconst, bias_addr, valid);
       }
       // row max over both halves (partner = same lane of warp +-4)
-      float* ex = sMx + (j & 1) * 2 * AQ;
-      ex[half * AQ + row] = mx;
+      const uint32_t ex = sMx_addr + static_cast<uint32_t>((j & 1) * 2 * AQ) * 4u;
+      sts_f32(ex + (half * AQ + row) * 4u, mx);
       pair_barrier(1 + quad);
-      mx = fmaxf(mx, ex[(half ^ 1) * AQ + row]);
+      mx = fmaxf(mx, lds_f32(ex + ((half ^ 1) * AQ + row) * 4u));
       if (j == 0) {
         m_ref = mx;
       } else {
@@ -263,7 +268,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           psum2 = fadd2(psum2, pack2(p0, p1));
           pk[i] = pack_bf16x2(p0, p1);
         }
-        *reinterpret_cast<uint4*>(prow + (((half * 4 + ch) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        sts_v4(prow + (((half * 4 + ch) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
       }
       float ps0, ps1;
       unpack2(psum2, ps0, ps1);
@@ -274,10 +279,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     }
     // ---- finalize: O / l -> bf16 -> (B, T, d) at [b, q, h*64 + half*32 ..]
     {
-      float* ex = sMx + (nblk & 1) * 2 * AQ;
-      ex[half * AQ + row] = l;
+      const uint32_t ex = sMx_addr + static_cast<uint32_t>((nblk & 1) * 2 * AQ) * 4u;
+      sts_f32(ex + (half * AQ + row) * 4u, l);
       pair_barrier(1 + quad);
-      l += ex[(half ^ 1) * AQ + row];
+      l += lds_f32(ex + ((half ^ 1) * AQ + row) * 4u);
     }
     mbar_wait(&p_free[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1, 560);
     tc_fence_after();
