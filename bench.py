@@ -187,17 +187,8 @@ def broadcast_weights(models, world):
     """NCCL over NVLink: rank 0's weights to every rank, one flat blob per model (the only collective on this path)."""
     if world == 1:
         return
-    import torch.distributed as dist
-    for m in models:
-        params = [p for p in m.parameters()]
-        flat = torch.cat([p.data.reshape(-1).float() for p in params])
-        dist.broadcast(flat, src=0)
-        off = 0
-        for p in params:
-            n = p.numel()
-            p.data.copy_(flat[off:off + n].view_as(p))
-            off += n
-        m._invalidate()
+    from vampnet_b200.parallel import broadcast_module_weights
+    broadcast_module_weights(models, src=0)
 
 
 def main():

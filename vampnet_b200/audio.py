@@ -203,23 +203,20 @@ def _k_weight(x, sr):
     N = x.shape[-1]
     nfft = 1 << (N + 4096 - 1).bit_length()
     w = torch.arange(nfft // 2 + 1, device=x.device, dtype=torch.float64) * (2 * math.pi / nfft)
-    # pre-filter: high shelf +4 dB at 1681.97 Hz, Q 0.7072
-    G, Q, fc = 3.99984385397, 0.7071752369554193, 1681.9744509555319
-    A = 10 ** (G / 40.0)
-    w0 = 2 * math.pi * fc / sr
-    alpha = math.sin(w0) / (2 * Q)
-    cw = math.cos(w0)
-    b1 = [A * ((A + 1) + (A - 1) * cw + 2 * math.sqrt(A) * alpha), -2 * A * ((A - 1) + (A + 1) * cw),
-          A * ((A + 1) + (A - 1) * cw - 2 * math.sqrt(A) * alpha)]
-    a1 = [(A + 1) - (A - 1) * cw + 2 * math.sqrt(A) * alpha, 2 * ((A - 1) - (A + 1) * cw),
-          (A + 1) - (A - 1) * cw - 2 * math.sqrt(A) * alpha]
-    # RLB: high-pass at 38.1355 Hz, Q 0.5003
-    Q2, fc2 = 0.5003270373253953, 38.13547087613982
-    w02 = 2 * math.pi * fc2 / sr
-    alpha2 = math.sin(w02) / (2 * Q2)
-    cw2 = math.cos(w02)
-    b2 = [(1 + cw2) / 2, -(1 + cw2), (1 + cw2) / 2]
-    a2 = [1 + alpha2, -2 * cw2, 1 - alpha2]
+    # Stage 1, shelving pre-filter, and stage 2, RLB high-pass: the BS.1770 48 kHz biquads re-derived for any
+    # sample rate through the bilinear-transform parameters (f0, G, Q) that reproduce the standard's table.
+    f0, G, Q = 1681.974450955533, 3.999843853973347, 0.7071752369554196
+    K = math.tan(math.pi * f0 / sr)
+    Vh = 10.0 ** (G / 20.0)
+    Vb = Vh ** 0.4996667741545416
+    a0 = 1.0 + K / Q + K * K
+    b1 = [(Vh + Vb * K / Q + K * K) / a0, 2.0 * (K * K - Vh) / a0, (Vh - Vb * K / Q + K * K) / a0]
+    a1 = [1.0, 2.0 * (K * K - 1.0) / a0, (1.0 - K / Q + K * K) / a0]
+    f0, Q = 38.13547087602444, 0.5003270373238773
+    K = math.tan(math.pi * f0 / sr)
+    a0 = 1.0 + K / Q + K * K
+    b2 = [1.0, -2.0, 1.0]
+    a2 = [1.0, 2.0 * (K * K - 1.0) / a0, (1.0 - K / Q + K * K) / a0]
     H = (_biquad_response(b1, a1, w) * _biquad_response(b2, a2, w)).to(torch.complex64)
     X = torch.fft.rfft(x.float(), n=nfft)
     return torch.fft.irfft(X * H, n=nfft)[..., :N]
