@@ -134,9 +134,11 @@ class CodebookEmbedding(nn.Module):
         n = self.n_codebooks if n is None else n
         tabs = []
         for i in range(n):
-            cb = codec.quantizer.quantizers[i].codebook.weight
-            tabs.append(torch.cat([cb.to(self.special["MASK"].device, torch.float32),
-                                   self.special["MASK"][i:i + 1].float()], dim=0))
+            cb = codec.quantizer.quantizers[i].codebook.weight.to(self.special["MASK"].device, torch.float32)
+            # MASK rows exist only for this model's own codebooks; decode() of more codebooks than that
+            # (reference transformer.py:672 with the 4-codebook coarse model and 14-codebook z) never indexes them
+            extra = self.special["MASK"][i:i + 1].float() if i < self.n_codebooks else torch.zeros_like(cb[:1])
+            tabs.append(torch.cat([cb, extra], dim=0))
         return torch.stack(tabs, 0)
 
     def from_codes(self, codes: torch.Tensor, codec) -> torch.Tensor:
