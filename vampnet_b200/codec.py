@@ -7,7 +7,7 @@ vampnet/interface.py:16):  DAC.load, .preprocess, .encode(...)["codes"], .decode
 layers.py:145).  ``lac`` is an un-vendored, unpinned third-party fork of the Descript Audio Codec whose
 source and checkpoints are not available here; the architecture below is the published DAC (encoder
 dim 64, strides (2,4,8,12) -> hop 768, 14 x 1024 x 8 RVQ, decoder dim 1536) with hyper-parameters read
-from the checkpoint's metadata when one is loaded.  Parameter names follow the oracle / HF layout
+from the checkpoint's metadata when one is loaded.  Parameter names follow the HF DacModel layout
 (encoder.block.{i}.res_unit{r}.conv1.weight ...); weight-norm pairs (weight_g / weight_v) are folded
 on load.
 
@@ -170,7 +170,7 @@ class DAC(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def load_flat(self, weights: Dict[str, torch.Tensor]):
-        """Load a flat {dotted name: tensor} dict (oracle / HF naming).  weight_g / weight_v pairs are folded."""
+        """Load a flat {dotted name: tensor} dict (HF DacModel naming).  weight_g / weight_v pairs are folded."""
         weights = dict(weights)
         for k in [k for k in weights if k.endswith(".weight_v")]:
             base = k[: -len("_v")]
