@@ -41,15 +41,18 @@ typedef struct vnb_weights {
   const float* emb_table;  /* (C, V+1, 8)  codec codebooks with the learned MASK row appended (layers.py:145-150) */
   const float* emb_wt;     /* (8C, d)      embedding.out_proj.weight transposed (layers.py:132) */
   const float* emb_b;      /* (d) */
-  const float* norm1;      /* (L, d)       norm_1.weight */
-  const void* wqkv;        /* (L, 3d, d)   bf16, rows = [w_qs | w_ks | w_vs] (transformer.py:109-114) */
+  const float* norm1;      /* (L, d)       norm_1.weight (kept for vnb_op_rmsnorm; the forward uses the folded form) */
+  const void* wqkv;        /* (L, 3d, d)   bf16, rows = [w_qs | w_ks | w_vs] (transformer.py:109-114), columns scaled
+                                           by norm_1.weight: RMSNorm (transformer.py:43-58) is fused, the kernels
+                                           apply rsqrt(mean(x^2)+eps) as a row scale of the GEMM result */
   const void* wo;          /* (L, d, d)    bf16, fc */
   const float* norm3;      /* (L, d)       norm_3.weight */
-  const void* w1;          /* (L, 4d, d)   bf16, feed_forward.w_1 with rows interleaved per 256-row tile:
+  const void* w1;          /* (L, 4d, d)   bf16, feed_forward.w_1 (columns scaled by norm_3.weight) with rows interleaved per 256-row tile:
                                            [128 value rows | 128 gate rows] (activations.py:33-35) */
   const void* w2;          /* (L, d, 2d)   bf16, feed_forward.w_2 */
   const float* norm_f;     /* (d)          transformer.norm.weight */
-  const void* wcls;        /* (Cp*V, d)    bf16, classifier g*v/|v| with rows permuted to c*V + p (transformer.py:634) */
+  const void* wcls;        /* (Cp*V, d)    bf16, classifier g*v/|v| (columns scaled by transformer.norm.weight) with rows
+                                           permuted to c*V + p (transformer.py:634) */
   const float* bcls;       /* (Cp*V)       permuted the same way */
   const float* rel_bias;   /* (2*rel_sat+1, H) fp32: bias for clamp(key-query, -rel_sat, rel_sat) (transformer.py:123-209) */
   int32_t rel_sat;

@@ -179,20 +179,26 @@ class OracleVampNet:
         self.layers = []
         for i in range(L):
             p = f"transformer.layers.{i}."
+            n1, n3 = self.sd[p + "norm_1.weight"], self.sd[p + "norm_3.weight"]
+            # bf16 mode mirrors the kernels: the RMSNorm weight is folded into the following projection
+            # (W * w[None, :], then rounded to bf16) and the 1/rms factor is applied to the GEMM result.
+            f1 = n1[None, :] if mode == "bf16" else 1.0
+            f3 = n3[None, :] if mode == "bf16" else 1.0
             self.layers.append(dict(
-                norm_1=self.sd[p + "norm_1.weight"],
-                wq=q(fold_lora(self.sd, p + "self_attn.w_qs")),
-                wk=q(self.sd[p + "self_attn.w_ks.weight"]),
-                wv=q(fold_lora(self.sd, p + "self_attn.w_vs")),
+                norm_1=n1,
+                wq=q(fold_lora(self.sd, p + "self_attn.w_qs") * f1),
+                wk=q(self.sd[p + "self_attn.w_ks.weight"] * f1),
+                wv=q(fold_lora(self.sd, p + "self_attn.w_vs") * f1),
                 wo=q(fold_lora(self.sd, p + "self_attn.fc")),
-                norm_3=self.sd[p + "norm_3.weight"],
-                w1=q(fold_lora(self.sd, p + "feed_forward.w_1")),
+                norm_3=n3,
+                w1=q(fold_lora(self.sd, p + "feed_forward.w_1") * f3),
                 w2=q(fold_lora(self.sd, p + "feed_forward.w_2")),
             ))
         self.rel_bias = self.sd["transformer.layers.0.self_attn.relative_attention_bias.weight"]  # (32, H)
         self.final_norm = self.sd["transformer.norm.weight"]
+        fc = self.final_norm[None, :] if mode == "bf16" else 1.0
         self.cls_w = q(weight_norm_fold(self.sd["classifier.layers.0.weight_g"],
-                                        self.sd["classifier.layers.0.weight_v"]).squeeze(-1))
+                                        self.sd["classifier.layers.0.weight_v"]).squeeze(-1) * fc)
         self.cls_b = self.sd["classifier.layers.0.bias"]
         self.emb_w = self.sd["embedding.out_proj.weight"].squeeze(-1)  # (d, C*8), stays fp32 in both modes
         self.emb_b = self.sd["embedding.out_proj.bias"]
@@ -224,14 +230,15 @@ class OracleVampNet:
         return self.rel_bias[buckets].permute(2, 0, 1)
 
     # ---- A10: MultiHeadRelativeAttention.forward (transformer.py:211-257) ---------------
-    def attention(self, y: torch.Tensor, lw: dict, bias: torch.Tensor) -> torch.Tensor:
+    def attention(self, y: torch.Tensor, lw: dict, bias: torch.Tensor, rs=1.0) -> torch.Tensor:
+        """y: normed input (fp32 mode) or the raw residual stream with rs = 1/rms per row (bf16 mode)."""
         B, T, d = y.shape
         H = self.cfg.n_heads
         dh = d // H
         ya = self.qa(y)
-        q = self.qa(ya @ lw["wq"].t()).view(B, T, H, dh).permute(2, 0, 1, 3)  # (H, B, T, dh)
-        k = self.qa(ya @ lw["wk"].t()).view(B, T, H, dh).permute(2, 0, 1, 3)
-        v = self.qa(ya @ lw["wv"].t()).view(B, T, H, dh).permute(2, 0, 1, 3)
+        q = self.qa((ya @ lw["wq"].t()) * rs).view(B, T, H, dh).permute(2, 0, 1, 3)  # (H, B, T, dh)
+        k = self.qa((ya @ lw["wk"].t()) * rs).view(B, T, H, dh).permute(2, 0, 1, 3)
+        v = self.qa((ya @ lw["wv"].t()) * rs).view(B, T, H, dh).permute(2, 0, 1, 3)
         s = torch.matmul(q, k.transpose(-1, -2)) / np.sqrt(dh)  # (H, B, T, T)
         s = s + bias[:, None]
         # x_mask is all ones on this path (transformer.py:619) -> masked_fill is a no-op
@@ -247,8 +254,8 @@ class OracleVampNet:
         return self.qa(o) @ lw["wo"].t()
 
     # ---- A12: FeedForward + GatedGELU (transformer.py:72-85, activations.py:16-35) ------
-    def ffn(self, y: torch.Tensor, lw: dict) -> torch.Tensor:
-        h = self.qa(y) @ lw["w1"].t()
+    def ffn(self, y: torch.Tensor, lw: dict, rs=1.0) -> torch.Tensor:
+        h = (self.qa(y) @ lw["w1"].t()) * rs
         p1, p2 = h.chunk(2, dim=-1)  # gate is the second half
         gelu = 0.5 * p2 * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (p2 + 0.044715 * torch.pow(p2, 3.0))))
         return self.qa(p1 * gelu) @ lw["w2"].t()
@@ -260,11 +267,17 @@ class OracleVampNet:
         B, _, T = latents.shape
         x = torch.einsum("bkt,nk->btn", latents.float(), self.emb_w) + self.emb_b  # Conv1d k=1 (layers.py:162)
         bias = self.position_bias(T)
-        for lw in self.layers:  # TransformerLayer.forward (transformer.py:314-369); FiLM is identity (d_cond=0)
-            x = x + self.attention(self.rmsnorm(x, lw["norm_1"]), lw, bias)
-            x = x + self.ffn(self.rmsnorm(x, lw["norm_3"]), lw)
-        hfin = self.rmsnorm(x, self.final_norm)
-        out = self.qa(hfin) @ self.cls_w.t() + self.cls_b  # (B, T, V*Cp), channel = p*Cp + c
+        if self.mode == "fp32":
+            for lw in self.layers:  # TransformerLayer.forward (transformer.py:314-369); FiLM is identity (d_cond=0)
+                x = x + self.attention(self.rmsnorm(x, lw["norm_1"]), lw, bias)
+                x = x + self.ffn(self.rmsnorm(x, lw["norm_3"]), lw)
+            out = self.rmsnorm(x, self.final_norm) @ self.cls_w.t() + self.cls_b  # (B, T, V*Cp), channel = p*Cp + c
+        else:
+            inv_rms = lambda t: torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6)
+            for lw in self.layers:
+                x = x + self.attention(x, lw, bias, inv_rms(x))
+                x = x + self.ffn(x, lw, inv_rms(x))
+            out = (self.qa(x) @ self.cls_w.t()) * inv_rms(x) + self.cls_b
         Cp, V = cfg.n_predict_codebooks, cfg.vocab_size
         # "b (p c) t -> b p (t c)" (transformer.py:634)
         logits = out.view(B, T, V, Cp).permute(0, 2, 1, 3).reshape(B, V, T * Cp)

@@ -133,7 +133,8 @@ struct GraphKey {  // graphs bake pointers, so generate() stages z/mask/out in w
 
 struct Workspace {
   int B = 0, T = 0, Tpad = 0, M = 0;
-  DevBuf x, y, qk, vT, att, h, logits, zcur, zorig, tokens, conf, n0, dyn, z_in, mask_in, z_out;
+  DevBuf x, y, qk, vT, att, h, logits, zcur, zorig, tokens, conf, n0, dyn, z_in, mask_in, z_out, ssA, ssB;
+  int ss_parts = 0;
   std::vector<GemmPlan> qkv, wo, up, down;
   GemmPlan cls;
   AttnPlan attn;
@@ -189,7 +190,10 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   ws->B = B; ws->T = T; ws->M = B * T; ws->Tpad = (T + 7) / 8 * 8;
   const size_t M = ws->M;
   CK(ws->x.alloc(M * d * 4));
-  CK(ws->y.alloc(M * d * 2));
+  CK(ws->y.alloc(M * d * 2));  // bf16 copy of the residual stream (A operand of QKV / FFN-up / classifier)
+  ws->ss_parts = d / 256;     // one partial row-sum-of-squares per 256-column tile of the producing GEMM
+  CK(ws->ssA.alloc(M * ws->ss_parts * 4, true));
+  CK(ws->ssB.alloc(M * ws->ss_parts * 4, true));
   CK(ws->qk.alloc(M * 2 * d * 2));
   CK(ws->vT.alloc(static_cast<size_t>(B) * d * ws->Tpad * 2, /*zero=*/true));  // padding keys stay 0 forever
   CK(ws->att.alloc(M * d * 2));
@@ -210,7 +214,11 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   const __nv_bfloat16* w2 = reinterpret_cast<const __nv_bfloat16*>(m->w.w2);
   ws->qkv.resize(L); ws->wo.resize(L); ws->up.resize(L); ws->down.resize(L);
   const size_t dd = static_cast<size_t>(d) * d;
+  const float inv_d = 1.0f / static_cast<float>(d), eps = 1e-6f;
+  auto consumer = [&](GemmPlan& p, const DevBuf& ss) { p.ss_in = ss.as<float>(); p.ss_parts = ws->ss_parts; p.inv_d = inv_d; p.eps = eps; };
+  auto producer = [&](GemmPlan& p, const DevBuf& ss) { p.out_bf16 = ws->y.p; p.ss_out = ss.as<float>(); };
   for (int l = 0; l < L; ++l) {
+    // residual stream x (fp32) + its bf16 copy y + row sums of squares: ssA feeds QKV, ssB feeds FFN-up
     bool ok = make_gemm_plan(&ws->qkv[l], VNB_EPI_QKV, ws->y.p, wqkv + l * 3 * dd, ws->M, 3 * d, d, ws->qk.p, ws->vT.p,
                              nullptr, T, ws->Tpad, 2 * d) &&
               make_gemm_plan(&ws->wo[l], VNB_EPI_RESID, ws->att.p, wo + l * dd, ws->M, d, d, ws->x.p, nullptr, nullptr, T,
@@ -220,10 +228,15 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
               make_gemm_plan(&ws->down[l], VNB_EPI_RESID, ws->h.p, w2 + l * 2 * dd, ws->M, d, 2 * d, ws->x.p, nullptr,
                              nullptr, T, ws->Tpad, 0);
     if (!ok) return fail("plan layer %d: %s", l, tmap_error());
+    consumer(ws->qkv[l], ws->ssA);
+    producer(ws->wo[l], ws->ssB);
+    consumer(ws->up[l], ws->ssB);
+    producer(ws->down[l], ws->ssA);
   }
   if (!make_gemm_plan(&ws->cls, VNB_EPI_BIAS_F32, ws->y.p, m->w.wcls, ws->M, Cp * c.vocab_size, d, ws->logits.p, nullptr,
                       m->w.bcls, T, ws->Tpad, 0))
     return fail("plan classifier: %s", tmap_error());
+  consumer(ws->cls, ws->ssA);
   if (!make_attn_plan(&ws->attn, ws->qk.p, ws->vT.p, ws->att.p, m->w.rel_bias, m->w.rel_sat, B, T, ws->Tpad, c.n_heads))
     return fail("plan attention: %s", tmap_error());
   *out = ws.get();
@@ -241,18 +254,16 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
 // x already holds the embedded input; runs the L layers + final norm + classifier into `logits`.
 static int run_stack(vnb_model* m, Workspace* ws, float* logits, cudaStream_t st) {
   const vnb_config& c = m->cfg;
-  const int d = c.d_model;
-  const float eps = 1e-6f;
+  // RMSNorm (transformer.py:43-58) is fused: norm weights are folded into wqkv / w1 / wcls at pack time, the
+  // producers of x (embed, attn-out, ffn-down) also emit bf16(x) and per-row sums of squares, and the consumers
+  // scale their accumulator rows by rsqrt(mean(x^2) + eps).
   for (int l = 0; l < c.n_layers; ++l) {
-    LAUNCH(FAM_RMSNORM, launch_rmsnorm(ws->x.as<float>(), m->w.norm1 + static_cast<size_t>(l) * d, ws->y.p, ws->M, d, eps, st));
     LAUNCH(FAM_GEMM_QKV, launch_gemm(ws->qkv[l], st));
     LAUNCH(FAM_ATTN, launch_attention(ws->attn, st));
     LAUNCH(FAM_GEMM_O, launch_gemm(ws->wo[l], st));
-    LAUNCH(FAM_RMSNORM, launch_rmsnorm(ws->x.as<float>(), m->w.norm3 + static_cast<size_t>(l) * d, ws->y.p, ws->M, d, eps, st));
     LAUNCH(FAM_GEMM_UP, launch_gemm(ws->up[l], st));
     LAUNCH(FAM_GEMM_DOWN, launch_gemm(ws->down[l], st));
   }
-  LAUNCH(FAM_RMSNORM, launch_rmsnorm(ws->x.as<float>(), m->w.norm_f, ws->y.p, ws->M, d, eps, st));
   GemmPlan cls = ws->cls;
   cls.out = logits;
   LAUNCH(FAM_GEMM_CLS, launch_gemm(cls, st));
@@ -302,7 +313,7 @@ int32_t vnb_forward_codes(vnb_model* m, const int64_t* codes, int32_t B, int32_t
   LAUNCH(FAM_STATE, launch_gen_init(codes, nullptr, ws->zcur.as<int32_t>(), ws->zorig.as<int32_t>(), ws->n0.as<int32_t>(), B,
                      c.n_codebooks, T, /*ncc=*/c.n_codebooks, c.vocab_size, st));
   LAUNCH(FAM_EMBED, launch_embed_codes(ws->zcur.as<int32_t>(), m->w.emb_table, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), ws->M,
-                        c.n_codebooks, c.vocab_size + 1, c.d_model, st));
+                        c.n_codebooks, c.vocab_size + 1, c.d_model, st, ws->y.p, ws->ssA.as<float>(), ws->ss_parts));
   m->last = ws;
   return run_stack(m, ws, logits, st);
 }
@@ -312,7 +323,8 @@ int32_t vnb_forward_latents(vnb_model* m, const float* latents, int32_t B, int32
   Workspace* ws;
   if (get_workspace(m, B, T, &ws)) return 1;
   const vnb_config& c = m->cfg;
-  LAUNCH(FAM_EMBED, launch_embed_latents(latents, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), B, T, c.n_codebooks * 8, c.d_model, st));
+  LAUNCH(FAM_EMBED, launch_embed_latents(latents, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), B, T, c.n_codebooks * 8, c.d_model, st,
+                                          ws->y.p, ws->ssA.as<float>(), ws->ss_parts));
   m->last = ws;
   return run_stack(m, ws, logits, st);
 }
@@ -339,7 +351,7 @@ static int enqueue_generate(vnb_model* m, Workspace* ws, const int64_t* z, const
   sa.B = ws->B; sa.T = ws->T; sa.C = c.n_codebooks; sa.ncc = ncc; sa.V = c.vocab_size; sa.mask_token = c.vocab_size;
   for (int i = 0; i < steps; ++i) {
     LAUNCH(FAM_EMBED, launch_embed_codes(ws->zcur.as<int32_t>(), m->w.emb_table, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), ws->M,
-                          c.n_codebooks, c.vocab_size + 1, c.d_model, st));
+                          c.n_codebooks, c.vocab_size + 1, c.d_model, st, ws->y.p, ws->ssA.as<float>(), ws->ss_parts));
     if (run_stack(m, ws, ws->logits.as<float>(), st)) return 1;
     LAUNCH(FAM_SAMPLE, launch_sample_step_dev(sa, ws->dyn.as<SampleDyn>() + i, st));
     ++g_launches;  // sample step = two kernels

@@ -63,8 +63,10 @@ template <bool FROM_CODES>
 __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ codes, const float* __restrict__ lat_in,
                                                     const float* __restrict__ table, const float* __restrict__ wt,
                                                     const float* __restrict__ bias, float* __restrict__ x, int M, int T,
-                                                    int C, int V1, int K, int d) {
+                                                    int C, int V1, int K, int d, __nv_bfloat16* __restrict__ xb,
+                                                    float* __restrict__ ss, int ss_parts) {
   __shared__ float lat[EMB_ROWS][EMB_MAXK];
+  __shared__ float red[8][EMB_ROWS];
   const int m0 = blockIdx.x * EMB_ROWS;
   for (int i = threadIdx.x; i < EMB_ROWS * K; i += blockDim.x) {
     const int r = i / K, k = i - r * K;
@@ -83,6 +85,9 @@ __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ 
     lat[r][k] = v;
   }
   __syncthreads();
+  float ssr[EMB_ROWS];
+#pragma unroll
+  for (int r = 0; r < EMB_ROWS; ++r) ssr[r] = 0.f;
   for (int n = threadIdx.x; n < d; n += blockDim.x) {
     float acc[EMB_ROWS];
     const float bn = bias[n];
@@ -94,24 +99,44 @@ __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ 
       for (int r = 0; r < EMB_ROWS; ++r) acc[r] = fmaf(wv, lat[r][k], acc[r]);
     }
 #pragma unroll
-    for (int r = 0; r < EMB_ROWS; ++r)
-      if (m0 + r < M) x[static_cast<size_t>(m0 + r) * d + n] = acc[r] + bn;
+    for (int r = 0; r < EMB_ROWS; ++r) {
+      if (m0 + r < M) {
+        const float v = acc[r] + bn;
+        x[static_cast<size_t>(m0 + r) * d + n] = v;
+        if (xb) xb[static_cast<size_t>(m0 + r) * d + n] = __float2bfloat16_rn(v);
+        ssr[r] += v * v;
+      }
+    }
+  }
+  if (ss) {  // row sums of squares for the RMSNorm fused into the next GEMM (fixed reduction order)
+#pragma unroll
+    for (int r = 0; r < EMB_ROWS; ++r) {
+      const float v = warp_sum(ssr[r]);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][r] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < EMB_ROWS && m0 + threadIdx.x < M) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+      ss[m0 + threadIdx.x] = t;
+      for (int p = 1; p < ss_parts; ++p) ss[static_cast<size_t>(p) * M + m0 + threadIdx.x] = 0.f;
+    }
   }
 }
 
 cudaError_t launch_embed_codes(const int32_t* codes_btc, const float* table, const float* wt, const float* b, float* x,
-                               int M, int C, int V1, int d, cudaStream_t st) {
+                               int M, int C, int V1, int d, cudaStream_t st, void* xb, float* ss, int ss_parts) {
   if (C * 8 > EMB_MAXK) return cudaErrorInvalidValue;
-  embed_kernel<true><<<(M + EMB_ROWS - 1) / EMB_ROWS, 256, 0, st>>>(codes_btc, nullptr, table, wt, b, x, M, 1, C, V1,
-                                                                    C * 8, d);
+  embed_kernel<true><<<(M + EMB_ROWS - 1) / EMB_ROWS, 256, 0, st>>>(
+      codes_btc, nullptr, table, wt, b, x, M, 1, C, V1, C * 8, d, reinterpret_cast<__nv_bfloat16*>(xb), ss, ss_parts);
   return cudaGetLastError();
 }
 cudaError_t launch_embed_latents(const float* lat, const float* wt, const float* b, float* x, int B, int T, int K,
-                                 int d, cudaStream_t st) {
+                                 int d, cudaStream_t st, void* xb, float* ss, int ss_parts) {
   if (K > EMB_MAXK) return cudaErrorInvalidValue;
   const int M = B * T;
-  embed_kernel<false><<<(M + EMB_ROWS - 1) / EMB_ROWS, 256, 0, st>>>(nullptr, lat, nullptr, wt, b, x, M, T, K / 8, 0,
-                                                                     K, d);
+  embed_kernel<false><<<(M + EMB_ROWS - 1) / EMB_ROWS, 256, 0, st>>>(
+      nullptr, lat, nullptr, wt, b, x, M, T, K / 8, 0, K, d, reinterpret_cast<__nv_bfloat16*>(xb), ss, ss_parts);
   return cudaGetLastError();
 }
 

@@ -37,6 +37,12 @@ struct GemmArgs {
   const float* bias;  // EPI_BIAS_F32
   int T, Tpad;        // EPI_QKV: rows m = b*T + t
   int d2;             // EPI_QKV: 2*d_model (column where V starts)
+  // ---- fused RMSNorm (reference transformer.py:43-58), see DESIGN.md §4 ----
+  __nv_bfloat16* out_bf16;  // EPI_RESID: bf16 copy of the updated residual stream (A operand of the next GEMM)
+  float* ss_out;            // EPI_RESID: (N/256, M) per-n-tile partial row sums of squares of the updated rows
+  const float* ss_in;       // consumers: partial row sums of squares of THEIR A operand; null = no row scaling
+  int ss_parts;             // number of partials to add (fixed order: deterministic)
+  float inv_d, eps;         // row scale = rsqrt(sum * inv_d + eps)
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -84,8 +90,9 @@ __device__ __forceinline__ void prefetch_addend(const GemmArgs& g, int lane, int
     for (int it = 0; it < 8; ++it) add[it] = b4;
   }
 }
+template <bool FUSED>
 __device__ __forceinline__ void drain_f32(const GemmArgs& g, const float* stg, int lane, int row_base, int col0,
-                                          const float4 (&add)[8]) {
+                                          const float4 (&add)[8], float (&ssacc)[8]) {
   const int c4 = (lane & 7) * 4;
   const int r0 = row_base + (lane >> 3);
   float* const base = reinterpret_cast<float*>(g.out) + static_cast<size_t>(r0) * g.N + col0 + c4;
@@ -94,7 +101,16 @@ __device__ __forceinline__ void drain_f32(const GemmArgs& g, const float* stg, i
   for (int it = 0; it < 8; ++it) {
     float4 a = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * STG_PITCH + c4);
     a.x += add[it].x; a.y += add[it].y; a.z += add[it].z; a.w += add[it].w;
-    if (r0 + it * 4 < g.M) *reinterpret_cast<float4*>(base + it * step) = a;
+    if (r0 + it * 4 < g.M) {
+      *reinterpret_cast<float4*>(base + it * step) = a;
+      if constexpr (FUSED) {
+        uint2 w;
+        w.x = pack_bf16x2(a.x, a.y);
+        w.y = pack_bf16x2(a.z, a.w);
+        *reinterpret_cast<uint2*>(g.out_bf16 + static_cast<size_t>(r0 + it * 4) * g.N + col0 + c4) = w;
+        ssacc[it] += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+      }
+    }
   }
   __syncwarp();
 }
@@ -228,11 +244,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         b_idx = row / g.T;
         t_idx = row - b_idx * g.T;
       }
+      float* stg = stg_all + quad * STG_FLOATS_PER_WARP;
+      const int row_base = m0 + quad * 32;
+      float rs = 1.0f;  // fused RMSNorm of the A operand: rsqrt(mean(x^2) + eps) of this thread's row
+      if (g.ss_in != nullptr && row_ok) {
+        float t = 0.f;
+        for (int p = 0; p < g.ss_parts; ++p) t += __ldg(g.ss_in + static_cast<size_t>(p) * g.M + row);
+        rs = rsqrtf(t * g.inv_d + g.eps);
+      }
+      float4 pre0[8];  // residual / bias of the first chunk: fetched while the mainloop of this tile still runs
+      if constexpr (EPI == VNB_EPI_RESID || EPI == VNB_EPI_BIAS_F32) prefetch_addend<EPI>(g, lane, row_base, n0, pre0);
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
-      float* stg = stg_all + quad * STG_FLOATS_PER_WARP;
-      const int row_base = m0 + quad * 32;
       if constexpr (EPI == VNB_EPI_GEGLU) {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -242,16 +266,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_wait_ld();
           float r[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]) * gelu_tanh(__uint_as_float(v2[j]));
+          for (int j = 0; j < 32; ++j) r[j] = (__uint_as_float(v[j]) * rs) * gelu_tanh(__uint_as_float(v2[j]) * rs);
           stage_rows(stg, lane, r);
           drain_bf16(reinterpret_cast<__nv_bfloat16*>(g.out), g.N / 2, g.M, stg, lane, row_base, (n0 >> 1) + c * 32);
+        }
+      } else if constexpr (EPI == VNB_EPI_RESID || EPI == VNB_EPI_BIAS_F32) {
+        // software-pipelined: the residual rows of chunk c+1 are in flight while chunk c is pulled out of TMEM,
+        // transposed and stored (the global-load latency would otherwise be paid 8 times per tile, serially)
+        const bool fused_out = (EPI == VNB_EPI_RESID) && g.out_bf16 != nullptr;
+        float ssacc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ssacc[i] = 0.f;
+        auto process = [&](int c, const float4 (&add)[8]) {
+          uint32_t v[32];
+          tmem_ld_x32(t_addr + c * 32, v);
+          tmem_wait_ld();
+          float r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]) * rs;  // rs == 1 unless a norm is fused in
+          stage_rows(stg, lane, r);
+          if (fused_out) drain_f32<true>(g, stg, lane, row_base, n0 + c * 32, add, ssacc);
+          else drain_f32<false>(g, stg, lane, row_base, n0 + c * 32, add, ssacc);
+        };
+        float4 addA[8], addB[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) addA[i] = pre0[i];
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; c += 2) {
+          prefetch_addend<EPI>(g, lane, row_base, n0 + (c + 1) * 32, addB);
+          process(c, addA);
+          if (c + 2 < BN / 32) prefetch_addend<EPI>(g, lane, row_base, n0 + (c + 2) * 32, addA);
+          process(c + 1, addB);
+        }
+        if (fused_out) {
+          // per-row sum of squares over this tile's 256 columns: 8 lanes share a row; fixed reduction order
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            float v = ssacc[it];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            const int rr = row_base + it * 4 + (lane >> 3);
+            if ((lane & 7) == 0 && rr < g.M) g.ss_out[static_cast<size_t>(n0 / BN) * g.M + rr] = v;
+          }
         }
       } else {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           const int col0 = n0 + c * 32;
-          float4 addend[8];
-          if constexpr (EPI == VNB_EPI_RESID || EPI == VNB_EPI_BIAS_F32) prefetch_addend<EPI>(g, lane, row_base, col0, addend);
           uint32_t v[32];
           tmem_ld_x32(t_addr + c * 32, v);
           tmem_wait_ld();
@@ -265,21 +327,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                    (static_cast<size_t>(b_idx) * d + (col0 - g.d2)) * g.Tpad + t_idx;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  o[static_cast<size_t>(j) * g.Tpad] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                  o[static_cast<size_t>(j) * g.Tpad] = __float2bfloat16_rn(__uint_as_float(v[j]) * rs);
               }
               continue;
             }
           }
           float r[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]) * rs;
           stage_rows(stg, lane, r);
           if constexpr (EPI == VNB_EPI_BF16) {
             drain_bf16(reinterpret_cast<__nv_bfloat16*>(g.out), g.N, g.M, stg, lane, row_base, col0);
-          } else if constexpr (EPI == VNB_EPI_QKV) {
-            drain_bf16(reinterpret_cast<__nv_bfloat16*>(g.out), g.d2, g.M, stg, lane, row_base, col0);
           } else {
-            drain_f32(g, stg, lane, row_base, col0, addend);
+            drain_bf16(reinterpret_cast<__nv_bfloat16*>(g.out), g.d2, g.M, stg, lane, row_base, col0);
           }
         }
       }
@@ -321,6 +381,8 @@ cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t st) {
   GemmArgs g;
   g.M = p.M; g.N = p.N; g.K = p.K; g.epi = p.epi; g.out = p.out; g.out2 = p.out2; g.bias = p.bias;
   g.T = p.T; g.Tpad = p.Tpad; g.d2 = p.d2;
+  g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p.out_bf16); g.ss_out = p.ss_out; g.ss_in = p.ss_in;
+  g.ss_parts = p.ss_parts; g.inv_d = p.inv_d; g.eps = p.eps;
   switch (p.epi) {
     case VNB_EPI_BF16: return launch_epi<VNB_EPI_BF16>(p.tmA, p.tmB, g, st);
     case VNB_EPI_QKV: return launch_epi<VNB_EPI_QKV>(p.tmA, p.tmB, g, st);

@@ -29,6 +29,12 @@ struct GemmPlan {
   void* out2 = nullptr;
   const float* bias = nullptr;
   int T = 1, Tpad = 1, d2 = 0;
+  // fused RMSNorm plumbing (see GemmArgs in gemm_tcgen05.cu)
+  void* out_bf16 = nullptr;
+  float* ss_out = nullptr;
+  const float* ss_in = nullptr;
+  int ss_parts = 0;
+  float inv_d = 0.f, eps = 0.f;
 };
 // Fills the tensor maps; A (M,K) bf16, W (N,K) bf16.
 bool make_gemm_plan(GemmPlan* p, int epi, const void* A, const void* W, int M, int N, int K, void* out, void* out2,
@@ -52,11 +58,13 @@ cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st);
 // ---- elementwise / gather ----
 cudaError_t launch_rmsnorm(const float* x, const float* w, void* y_bf16, int M, int d, float eps, cudaStream_t st);
 // codes_btc (B*T, C) int32  -> x (B*T, d) fp32
+// xb (bf16 copy of x) and ss (parts, M) row sums of squares (total in part 0, zeros elsewhere) are optional
 cudaError_t launch_embed_codes(const int32_t* codes_btc, const float* table, const float* wt, const float* b, float* x,
-                               int M, int C, int V1, int d, cudaStream_t st);
+                               int M, int C, int V1, int d, cudaStream_t st, void* xb = nullptr, float* ss = nullptr,
+                               int ss_parts = 0);
 // latents (B, K, T) fp32 -> x (B*T, d) fp32
 cudaError_t launch_embed_latents(const float* lat, const float* wt, const float* b, float* x, int B, int T, int K,
-                                 int d, cudaStream_t st);
+                                 int d, cudaStream_t st, void* xb = nullptr, float* ss = nullptr, int ss_parts = 0);
 
 // ---- generate-loop state kernels ----
 // z (B,C,T) int64, mask (B,C,T) int32|null -> zcur (B,T,C) int32 (masked), zorig (B,T,C) int32; n0 += count(MASK)

@@ -276,10 +276,13 @@ class VampNet(nn.Module):
         lay = self.transformer.layers
         p["norm1"] = torch.stack([l.norm_1.weight.float() for l in lay]).contiguous()
         p["norm3"] = torch.stack([l.norm_3.weight.float() for l in lay]).contiguous()
+        # RMSNorm is fused into the consuming GEMMs: norm weights are folded into the K axis of wqkv / w1 / wcls here,
+        # the kernels apply rsqrt(mean(x^2) + eps) as a row scale in their epilogues
         p["wqkv"] = torch.stack([torch.cat([l.self_attn.w_qs.folded(), l.self_attn.w_ks.weight.float(),
-                                            l.self_attn.w_vs.folded()], 0) for l in lay]).to(bf).contiguous()
+                                            l.self_attn.w_vs.folded()], 0) * l.norm_1.weight.float()[None, :]
+                                 for l in lay]).to(bf).contiguous()
         p["wo"] = torch.stack([l.self_attn.fc.folded() for l in lay]).to(bf).contiguous()
-        w1 = torch.stack([l.feed_forward.w_1.folded() for l in lay])  # (L, 4d, d): [value 2d | gate 2d]
+        w1 = torch.stack([l.feed_forward.w_1.folded() * l.norm_3.weight.float()[None, :] for l in lay])  # (L, 4d, d): [value 2d | gate 2d]
         nt = (2 * d) // 128
         val = w1[:, :2 * d].view(L, nt, 128, d)
         gate = w1[:, 2 * d:].view(L, nt, 128, d)
@@ -289,6 +292,7 @@ class VampNet(nn.Module):
         wn = self.classifier.layers[0]
         v = wn.weight_v.float().squeeze(-1)
         w = v * (wn.weight_g.float().view(-1, 1) / v.norm(dim=1, keepdim=True))
+        w = w * self.transformer.norm.weight.float()[None, :]
         # channel r = p*Cp + c  ->  row c*V + p, so a row-major (M, Cp*V) store IS (B, S = t*Cp + c, V)
         p["wcls"] = w.view(V, Cp, d).permute(1, 0, 2).reshape(Cp * V, d).to(bf).contiguous()
         p["bcls"] = wn.bias.float().view(V, Cp).t().reshape(-1).contiguous()
