@@ -171,7 +171,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -191,7 +191,27 @@ def broadcast_weights(models, world):
     broadcast_module_weights(models, src=0)
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner from C),
+    so fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
@@ -367,7 +387,7 @@ def main():
                 "value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
                 "sample": (f"1 coarse + 1 c2f sampling iteration at B=1,T=768 via the oracle port (fp32): "
                            f"{parts['coarse']:.2f}s + {parts['c2f']:.2f}s, extrapolated to 12+24 iterations per clip")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
