@@ -70,6 +70,7 @@ typedef struct vnb_gen_params {
   const int32_t* do_sample; /* host, [steps]: (i/steps) <= sample_cutoff */
   uint32_t seed_lo, seed_hi; /* Philox key */
   int32_t use_graph;        /* 1: capture the whole loop once per shape and replay it as a CUDA graph */
+  float top_p;              /* nucleus filtering on the raw logits (transformer.py:1001-1016); <=0 or >=1: off */
 } vnb_gen_params;
 
 int32_t vnb_abi_version(void);

@@ -101,7 +101,8 @@ def test_generate_greedy_bit_exact_given_logits(tag, cfgd, steps, graph):
 
 
 @pytest.mark.parametrize("tag,cfgd", [("coarse", TINY_COARSE), ("c2f", TINY_C2F)])
-@pytest.mark.parametrize("kw", [dict(), dict(temperature=0.8), dict(sample_cutoff=0.5, mask_temperature=3.0)])
+@pytest.mark.parametrize("kw", [dict(), dict(temperature=0.8), dict(sample_cutoff=0.5, mask_temperature=3.0),
+                                dict(temperature=0.9, top_p=0.85), dict(top_p=0.5, sample_cutoff=-1.0, mask_temperature=0.0)])
 def test_generate_sampled_matches_oracle_with_shared_noise(tag, cfgd, kw):
     """Sampling parity under the shared Philox stream: identical tokens except where the oracle's own
     decision margin is a numerical near-tie (libm vs CUDA logf/expf differ by ulps)."""

@@ -34,7 +34,7 @@ class GenParams(C.Structure):
     _fields_ = [
         ("sampling_steps", C.c_int32), ("temperature", C.c_float), ("gamma", C.POINTER(C.c_float)),
         ("temp_eff", C.POINTER(C.c_float)), ("do_sample", C.POINTER(C.c_int32)), ("seed_lo", C.c_uint32),
-        ("seed_hi", C.c_uint32), ("use_graph", C.c_int32),
+        ("seed_hi", C.c_uint32), ("use_graph", C.c_int32), ("top_p", C.c_float),
     ]
 
 

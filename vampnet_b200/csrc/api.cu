@@ -380,6 +380,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
     dyn[i].step = i;
     dyn[i].seed_lo = p->seed_lo;
     dyn[i].seed_hi = p->seed_hi;
+    dyn[i].top_p = p->top_p;
   }
   // pageable source: the runtime stages it before returning, so `dyn` may die at scope exit
   CK(cudaMemcpyAsync(ws->dyn.p, dyn.data(), sizeof(SampleDyn) * steps, cudaMemcpyHostToDevice, st));
@@ -459,7 +460,7 @@ int32_t vnb_sample_step(const float* logits, int32_t* zflat, int32_t* tokens_out
   SampleDyn d;
   d.inv_temp = temperature > 0.f ? static_cast<float>(1.0 / static_cast<double>(temperature)) : 1.0f;
   d.gamma = gamma; d.temp_eff = temp_eff; d.do_sample = do_sample; d.is_last = is_last; d.step = step;
-  d.seed_lo = seed_lo; d.seed_hi = seed_hi;
+  d.seed_lo = seed_lo; d.seed_hi = seed_hi; d.top_p = 0.f;
   SampleDyn* dd = scratch + (slot++ & 63);
   CK(cudaMemcpyAsync(dd, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   SampleArgs sa;

@@ -81,6 +81,7 @@ struct SampleDyn {
   float inv_temp, gamma, temp_eff;
   int do_sample, is_last, step;
   uint32_t seed_lo, seed_hi;
+  float top_p;  // <= 0 or >= 1: disabled (reference transformer.py:1001-1016)
 };
 struct SampleArgs {
   const float* logits;  // (B*S, V)

@@ -36,6 +36,11 @@ __device__ __forceinline__ float gumbel(float u) { return -logf(-logf(u)); }
 
 using SampleDynDev = SampleDyn;
 
+__device__ __forceinline__ uint32_t f2key(float f) {  // order-preserving float -> uint
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 struct SampleStatic {
   const float* logits;
   int32_t* zcur;
@@ -75,6 +80,51 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const SampleStatic a, 
       float4 v = lr[i * 32 + lane];
       x[i] = v;
       mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+  }
+  // nucleus (top-p) filtering on the RAW logits (reference transformer.py:1001-1016): sorted descending, a token is
+  // removed when the softmax mass of the tokens strictly before it exceeds top_p ("shift right by one" keeps the
+  // first token over the threshold).  Equivalent per-token rule: keep v iff sum_{u: x_u > x_v} p_u <= top_p.
+  // The smallest kept key is found by bisection over the order-preserving uint image of the floats.
+  if (dyn.top_p > 0.f && dyn.top_p < 1.f) {
+    const float gm = warp_max(mx);
+    float pr[MAXV4 * 4];
+    float ps = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV4; ++i) {
+      if (i < n4) {
+        const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { pr[i * 4 + j] = expf(xs[j] - gm); ps += pr[i * 4 + j]; }
+      }
+    }
+    ps = warp_sum(ps);
+    const float budget = dyn.top_p * ps;  // compare un-normalised masses
+    uint32_t lo = 0u, hi = 0xFFFFFFFFu;
+    for (int it = 0; it < 32; ++it) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      float above = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV4; ++i) {
+        if (i < n4) {
+          const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) above += f2key(xs[j]) > mid ? pr[i * 4 + j] : 0.f;
+        }
+      }
+      above = warp_sum(above);
+      if (above <= budget) hi = mid; else lo = mid + 1u;
+    }
+    mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < MAXV4; ++i) {
+      if (i < n4) {
+        if (f2key(x[i].x) < lo) x[i].x = -INFINITY;
+        if (f2key(x[i].y) < lo) x[i].y = -INFINITY;
+        if (f2key(x[i].z) < lo) x[i].z = -INFINITY;
+        if (f2key(x[i].w) < lo) x[i].w = -INFINITY;
+        mx = fmaxf(mx, fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w)));
+      }
     }
   }
   // arg-max of the raw logits (greedy) or of logits*inv_t + Gumbel (sampling), lowest index on ties
@@ -142,11 +192,6 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const SampleStatic a, 
     a.tokens[row] = best_i;
     a.conf[row] = cf;
   }
-}
-
-__device__ __forceinline__ uint32_t f2key(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
 __global__ void __launch_bounds__(1024) remask_kernel(const SampleStatic a, const SampleDynDev* __restrict__ dynp) {

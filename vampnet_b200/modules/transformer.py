@@ -408,8 +408,6 @@ class VampNet(nn.Module):
             raise NotImplementedError("ctrls/ctrl_masks: ControlEncoder is outside the hot path")
         if cfg_guidance is not None:
             raise NotImplementedError("cfg_guidance is dead code in the reference (transformer.py:845-847)")
-        if top_p is not None and top_p < 1.0:
-            raise NotImplementedError("top_p sampling is not implemented in the CUDA sampler yet")
         if seed is not None:  # at.util.seed(seed): process-global side effect callers rely on (transformer.py:711)
             random.seed(seed)
             np.random.seed(seed)
@@ -440,7 +438,7 @@ class VampNet(nn.Module):
         tef = (C.c_float * steps)(*[float(v) for v in temp_eff])
         dos = (C.c_int32 * steps)(*[1 if (i / steps) <= sample_cutoff else 0 for i in range(steps)])
         gp = _lib.GenParams(steps, float(temperature), gam, tef, dos, k & 0xFFFFFFFF, (k >> 32) & 0xFFFFFFFF,
-                            1 if self.use_cuda_graph else 0)
+                            1 if self.use_cuda_graph else 0, float(top_p) if (top_p is not None and top_p < 1.0) else 0.0)
         out = torch.empty_like(z)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().vnb_generate(self._handle, _lib.ptr(z), _lib.ptr(m32), B, T, C.byref(gp),
