@@ -157,7 +157,27 @@ int32_t vnb_codec_conv1d(const float* x, const float* w, const float* bias, cons
  * win (L,8,D), bin (L,8), wout (L,D,8), bout (L,D), cb (L,V,8) raw and cbn (L,V,8) L2-normalised codebooks. */
 int32_t vnb_codec_rvq(int32_t mode, const float* in_f, const int64_t* in_codes, const float* win, const float* bin,
                       const float* wout, const float* bout, const float* cb, const float* cbn, int64_t* codes, float* zq,
-                      float* latents, int32_t B, int32_t D, int32_t T, int32_t L, int32_t V, void* stream);
+                      float* latents, int32_t B, int32_t D, int32_t T, int32_t L, int32_t V, int32_t channels_last,
+                      void* zq_hi, void* zq_lo, void* stream);
+/* Tensor-core codec path (tcgen05, split-bf16 operands = fp32-grade products; see csrc/conv_tcgen05.cu).
+ * Activations are channels-last (B, T, C) and travel as hi/lo bf16 pairs (x = hi + lo).
+ *   y[b, q, n] = bias[n % bias_mod] + sum_tap sum_ci W[n, tap, ci] * a[b, q*s + tap*dil - pad, ci]   (+ resid)
+ * w_hi/w_lo: (N, taps * ceil(Cin/64) * 64) bf16, tap-major, channel blocks zero-padded to 64.
+ * Outputs (each optional): out_f32 = y, out_hi/out_lo = split(snake_alpha(y)) (alpha NULL: identity).
+ * Output element (q, n) of batch b lands at b*out_batch_stride + q*N + n + out_offset, and is dropped unless that
+ * flat index (without the batch term) is in [0, out_limit): this is how a transposed convolution with N = s*Cout
+ * phase-major columns writes its (T*s, Cout) result. */
+int32_t vnb_codec_conv_tc(const void* a_hi, const void* a_lo, int32_t B, int32_t Tin, int32_t Cin, int32_t s,
+                          const void* w_hi, const void* w_lo, int32_t N, int32_t taps, int32_t dil, int32_t pad,
+                          int32_t Tq, const float* bias, int32_t bias_mod, const float* alpha, int32_t alpha_mod,
+                          const float* resid, float* out_f32, void* out_hi, void* out_lo, int64_t out_batch_stride,
+                          int64_t out_offset, int64_t out_limit, int32_t do_tanh, void* stream);
+/* encoder.conv1 (Cin = 1): x (B,1,T) -> fp32 (B,T,C) + split snake_alpha(y);  decoder.conv2 (Cout = 1) + tanh. */
+int32_t vnb_codec_conv_in(const float* x, const float* w, const float* bias, const float* alpha, float* out_f32,
+                          void* out_hi, void* out_lo, int32_t B, int32_t T, int32_t C, int32_t K, int32_t pad,
+                          void* stream);
+int32_t vnb_codec_conv_out(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* audio, int32_t B,
+                           int32_t T, int32_t C, int32_t K, int32_t pad, void* stream);
 /* internal helper exported for the other translation units */
 int32_t vnb_set_error_cuda(const char* what, int32_t cuda_error);
 

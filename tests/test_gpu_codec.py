@@ -10,12 +10,15 @@ from oracle import dac_oracle as do
 pytestmark = pytest.mark.gpu
 
 
-def build(cfg, seed=0):
+PRECISIONS = ["tc", "fp32"]  # tcgen05 split-bf16 convolutions (default) and the fp32 CUDA-core kernels
+
+
+def build(cfg, seed=0, precision="tc"):
     from vampnet_b200.codec import DAC
     w = do.make_codec_weights(cfg, seed=seed)
     m = DAC(encoder_dim=cfg.encoder_dim, encoder_rates=cfg.encoder_rates, decoder_dim=cfg.decoder_dim,
             n_codebooks=cfg.n_codebooks, codebook_size=cfg.codebook_size, codebook_dim=cfg.codebook_dim,
-            sample_rate=cfg.sample_rate)
+            sample_rate=cfg.sample_rate, precision=precision)
     m.load_flat(w)
     return w, m.to("cuda")
 
@@ -23,8 +26,9 @@ def build(cfg, seed=0):
 SMALL = do.CodecConfig(encoder_dim=16, decoder_dim=128)
 
 
-def test_encoder_and_rvq_encode_small():
-    w, m = build(SMALL)
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_encoder_and_rvq_encode_small(precision):
+    w, m = build(SMALL, precision=precision)
     x = torch.randn(2, 1, 768 * 9 + 100, generator=torch.Generator().manual_seed(1)) * 0.3
     xp, n = do.preprocess(x, SMALL)
     xg, n2 = m.preprocess(x.cuda(), SMALL.sample_rate)
@@ -41,8 +45,9 @@ def test_encoder_and_rvq_encode_small():
     assert (got["latents"].cpu()[:, :8] - ref["latents"][:, :8]).abs().max() < 2e-4  # level 0 sees the same residual
 
 
-def test_decoder_small():
-    w, m = build(SMALL)
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_decoder_small(precision):
+    w, m = build(SMALL, precision=precision)
     zq = torch.randn(2, SMALL.latent_dim, 7, generator=torch.Generator().manual_seed(3))
     ref = do.decode(zq, w, SMALL)["audio"]
     got = m.decode(zq.cuda())["audio"].cpu()
@@ -69,10 +74,11 @@ def test_from_latents_and_from_codes():
     assert torch.equal(m.quantizer.quantizers[3].codebook.weight.cpu(), w["quantizer.quantizers.3.codebook.weight"])
 
 
-def test_full_size_layers():
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_full_size_layers(precision):
     """The real widths (64..1024 encoder, 1536..96 decoder) on a short clip."""
     cfg = do.CodecConfig()
-    w, m = build(cfg)
+    w, m = build(cfg, precision=precision)
     x = torch.randn(1, 1, 768 * 3, generator=torch.Generator().manual_seed(5)) * 0.3
     z_ref = do.encoder(x, w, cfg)
     enc = m.encode(x.cuda())

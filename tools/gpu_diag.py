@@ -212,6 +212,32 @@ def main():
         run_attention(2, 575, 4)
         run_attention(8, 768, 20, timing=True)
         run_attention(2, 3072, 20, timing=True)
+    elif stage == "codec":
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle import dac_oracle as do
+        from vampnet_b200.codec import DAC
+        cfg = do.CodecConfig()
+        prec = sys.argv[2] if len(sys.argv) > 2 else "tc"
+        m = DAC(precision=prec)
+        m.load_flat(do.make_codec_weights(cfg, seed=0))
+        m = m.to(dev)
+        print("precision", prec)
+        for B in (1, 4):
+            x = torch.randn(B, 1, 441600, device=dev) * 0.3
+            for _ in range(2):
+                enc = m.encode(x)
+                out = m.decode(enc["z"])
+            torch.cuda.synchronize()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            enc = m.encode(x)
+            e1.record()
+            out = m.decode(enc["z"])
+            e2.record()
+            torch.cuda.synchronize()
+            te, td = e0.elapsed_time(e1), e1.elapsed_time(e2)
+            print(f"codec B={B}: encode {te:.1f} ms ({0.612 * B / te * 1e3:.1f} TFLOP/s)  decode {td:.1f} ms "
+                  f"({1.369 * B / td * 1e3:.1f} TFLOP/s)  -> {B * 10.0 / ((te + td) * 1e-3):.1f}x real time", flush=True)
     elif stage == "attention_b32":
         run_attention(32, 768, 20, timing=True)
     else:

@@ -94,25 +94,32 @@ class _Quantizer:
     def quantizers(self):
         return list(self._codec.params._modules["quantizer"]._modules["quantizers"]._modules.values())
 
-    def _rvq(self, mode, in_f=None, in_codes=None):
+    def _rvq(self, mode, in_f=None, in_codes=None, channels_last=False, split=False):
+        """channels_last: z / zq are (B, T, D) (tensor-core codec path); split: also return zq as hi/lo bf16."""
         c = self._codec
         pk = c._packed()
         src = in_f if in_f is not None else in_codes
-        B, T = src.shape[0], src.shape[-1]
+        B = src.shape[0]
+        T = src.shape[1] if (channels_last and mode == 0) else src.shape[-1]
         dev = src.device
         D, L, V = c.latent_dim, c.n_codebooks, c.codebook_size
         if mode == 1:
             L = in_f.shape[1] // c.codebook_dim
         elif mode == 2:
             L = in_codes.shape[1]
-        zq = torch.empty(B, D, T, device=dev, dtype=torch.float32)
+        zq = torch.empty((B, T, D) if channels_last else (B, D, T), device=dev, dtype=torch.float32)
+        hi = torch.empty(B, T, D, device=dev, dtype=torch.bfloat16) if split else None
+        lo = torch.empty(B, T, D, device=dev, dtype=torch.bfloat16) if split else None
         codes = torch.empty(B, L, T, device=dev, dtype=torch.int64) if mode == 0 else None
         lat = torch.empty(B, L * c.codebook_dim, T, device=dev, dtype=torch.float32) if mode == 0 else None
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().vnb_codec_rvq(mode, _lib.ptr(in_f), _lib.ptr(in_codes), _lib.ptr(pk["win"]),
                                                 _lib.ptr(pk["bin"]), _lib.ptr(pk["wout"]), _lib.ptr(pk["bout"]),
                                                 _lib.ptr(pk["cb"]), _lib.ptr(pk["cbn"]), _lib.ptr(codes), _lib.ptr(zq),
-                                                _lib.ptr(lat), B, D, T, L, V, _lib.stream_ptr(dev)))
+                                                _lib.ptr(lat), B, D, T, L, V, 1 if channels_last else 0, _lib.ptr(hi),
+                                                _lib.ptr(lo), _lib.stream_ptr(dev)))
+        if split:
+            return zq, codes, lat, hi, lo
         return zq, codes, lat
 
     def __call__(self, z):
@@ -134,7 +141,7 @@ class _Quantizer:
 class DAC(nn.Module):
     def __init__(self, encoder_dim: int = 64, encoder_rates=(2, 4, 8, 12), latent_dim: int = None,
                  decoder_dim: int = 1536, decoder_rates=None, n_codebooks: int = 14, codebook_size: int = 1024,
-                 codebook_dim: int = 8, sample_rate: int = 44100, **_ignored):
+                 codebook_dim: int = 8, sample_rate: int = 44100, precision: str = "tc", **_ignored):
         super().__init__()
         self.encoder_dim = encoder_dim
         self.encoder_rates = tuple(encoder_rates)
@@ -145,6 +152,9 @@ class DAC(nn.Module):
         self.codebook_size = codebook_size
         self.codebook_dim = codebook_dim
         self.sample_rate = sample_rate
+        # "tc": tcgen05 tensor-core convolutions with split-bf16 operands (fp32-grade); "fp32": CUDA-core kernels
+        assert precision in ("tc", "fp32")
+        self.precision = precision
         self.hop_length = int(math.prod(self.encoder_rates))
         self._cfg = dict(encoder_dim=encoder_dim, encoder_rates=self.encoder_rates, latent_dim=self.latent_dim,
                          decoder_dim=decoder_dim, decoder_rates=self.decoder_rates, n_codebooks=n_codebooks,
@@ -222,8 +232,49 @@ class DAC(nn.Module):
         for i, s in enumerate(self.decoder_rates):
             w = P(f"decoder.block.{i}.conv_t1.weight")  # (cin, cout, 2s)
             pk[f"convt{i}"] = torch.stack([w[:, :, r::s].permute(1, 0, 2) for r in range(s)]).contiguous()
+        if self.precision == "tc":
+            self._pack_tc(pk)
         self._pack = pk
         return pk
+
+    # ---- tensor-core path: weights as (N, taps * cblocks * 64) split-bf16, tap-major -----------------------
+    @staticmethod
+    def _split(w: torch.Tensor):
+        hi = w.to(torch.bfloat16)
+        lo = (w - hi.float()).to(torch.bfloat16)
+        return hi.contiguous(), lo.contiguous()
+
+    def _pack_conv_tc(self, w: torch.Tensor):
+        """(Cout, Cin, K) -> (Cout, K * cblocks * 64)."""
+        co, ci, k = w.shape
+        cb = (ci + 63) // 64
+        t = torch.zeros(co, k, cb * 64, device=w.device, dtype=torch.float32)
+        t[:, :, :ci] = w.permute(0, 2, 1)
+        return self._split(t.reshape(co, k * cb * 64))
+
+    def _pack_convt_tc(self, w: torch.Tensor, s: int):
+        """ConvTranspose1d weight (Cin, Cout, 2s) -> (s*Cout, 2 * cblocks * 64): row r*Cout+co, tap j uses k = r + j*s."""
+        ci, co, k = w.shape
+        cb = (ci + 63) // 64
+        t = torch.zeros(s, co, 2, cb * 64, device=w.device, dtype=torch.float32)
+        for j in range(2):
+            t[:, :, j, :ci] = w[:, :, j * s:(j + 1) * s].permute(2, 1, 0)  # (r, co, ci)
+        return self._split(t.reshape(s * co, 2 * cb * 64))
+
+    def _pack_tc(self, pk):
+        P = self.params.get
+        for name in _layout(self._cfg):
+            if not name.endswith(".weight") or ".quantizer." in "." + name or name.endswith("codebook.weight"):
+                continue
+            base = name[:-len(".weight")]
+            w = P(name).float()
+            if base in ("encoder.conv1", "decoder.conv2"):
+                continue  # Cin = 1 / Cout = 1 edge layers run on CUDA cores
+            if ".conv_t1" in base:
+                idx = int(base.split(".")[2])
+                pk["tc:" + base] = self._pack_convt_tc(w, self.decoder_rates[idx])
+            else:
+                pk["tc:" + base] = self._pack_conv_tc(w)
 
     # ---- kernels -------------------------------------------------------------------------------
     def _conv(self, x, name, K, stride=1, dil=1, pad=0, alpha=None, resid=None, tanh=False, out=None):
@@ -271,6 +322,8 @@ class DAC(nn.Module):
         self._packed()
         x = audio_data.to(self.device, torch.float32).contiguous()
         P = self.params.get
+        if self.precision == "tc":
+            return self._encode_tc(x)
         with torch.cuda.device(self.device):
             h = self._conv(x, "encoder.conv1", 7, pad=3)
             for i, s in enumerate(self.encoder_rates):
@@ -288,6 +341,9 @@ class DAC(nn.Module):
         self._packed()
         P = self.params.get
         z = z.to(self.device, torch.float32).contiguous()
+        if self.precision == "tc":
+            audio = self._decode_tc(z)
+            return {"audio": audio if length is None else audio[..., :length]}
         with torch.cuda.device(self.device):
             h = self._conv(z, "decoder.conv1", 7, pad=3)
             for i, s in enumerate(self.decoder_rates):
@@ -297,6 +353,102 @@ class DAC(nn.Module):
                     h = self._res_unit(h, f"{p}.res_unit{r + 1}", dil)
             audio = self._conv(h, "decoder.conv2", 7, pad=3, alpha=P("decoder.snake1.alpha"), tanh=True)
         return {"audio": audio if length is None else audio[..., :length]}
+
+    # ---- tensor-core forward passes (activations channels-last, carried as fp32 stream + hi/lo bf16 operand) ----
+    def _tc(self, act, base, N, taps, dil, pad, Tq, s=1, alpha=None, alpha_mod=1, resid=None, out_f32=False,
+            out_split=True, bias_mod=None, out_rows=None, out_offset=0):
+        """One tcgen05 convolution.  act = (hi, lo) (B, Tin, Cin).  Returns (f32 | None, (hi, lo) | None)."""
+        hi, lo = act
+        B, Tin, Cin = hi.shape
+        wh, wl = self._pack["tc:" + base]
+        bias = self.params.get(base + ".bias")
+        out_rows = Tq if out_rows is None else out_rows
+        dev = hi.device
+        # output tensor geometry: normal conv (B, Tq, N); transposed conv (B, T*s, Cout) written through the
+        # (Tq, s*Cout) view shifted by out_offset
+        cout = bias.shape[0]
+        shape = (B, out_rows, cout)
+        f32 = resid if resid is not None else (torch.empty(shape, device=dev, dtype=torch.float32) if out_f32 else None)
+        oh = torch.empty(shape, device=dev, dtype=torch.bfloat16) if out_split else None
+        ol = torch.empty(shape, device=dev, dtype=torch.bfloat16) if out_split else None
+        _lib.check(_lib.lib().vnb_codec_conv_tc(
+            _lib.ptr(hi), _lib.ptr(lo), B, Tin, Cin, s, _lib.ptr(wh), _lib.ptr(wl), N, taps, dil, pad, Tq,
+            _lib.ptr(bias), cout if bias_mod is None else bias_mod, _lib.ptr(alpha), alpha_mod, _lib.ptr(resid),
+            _lib.ptr(f32) if (out_f32 or resid is not None) else None, _lib.ptr(oh), _lib.ptr(ol),
+            out_rows * cout, out_offset, out_rows * cout, 0, _lib.stream_ptr(dev)))
+        return f32, ((oh, ol) if out_split else None)
+
+    def _res_unit_tc(self, skip, act, name, dil, next_alpha):
+        """skip: fp32 stream (updated in place); act = split(snake1(skip)); returns split(next_alpha(skip'))."""
+        P = self.params.get
+        C = skip.shape[-1]
+        T = skip.shape[1]
+        _, a2 = self._tc(act, name + ".conv1", C, 7, dil, 3 * dil, T, alpha=P(name + ".snake2.alpha"), alpha_mod=C)
+        _, nxt = self._tc(a2, name + ".conv2", C, 1, 1, 0, T, alpha=next_alpha, alpha_mod=C, resid=skip)
+        return nxt
+
+    def _encode_tc(self, x):
+        P = self.params.get
+        B, _, N = x.shape
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            d = self.encoder_dim
+            skip = torch.empty(B, N, d, device=x.device, dtype=torch.float32)
+            hi = torch.empty(B, N, d, device=x.device, dtype=torch.bfloat16)
+            lo = torch.empty_like(hi)
+            _lib.check(lib.vnb_codec_conv_in(_lib.ptr(x), _lib.ptr(P("encoder.conv1.weight")),
+                                             _lib.ptr(P("encoder.conv1.bias")),
+                                             _lib.ptr(P("encoder.block.0.res_unit1.snake1.alpha")), _lib.ptr(skip),
+                                             _lib.ptr(hi), _lib.ptr(lo), B, N, d, 7, 3, _lib.stream_ptr(x.device)))
+            act = (hi, lo)
+            T = N
+            nb = len(self.encoder_rates)
+            for i, s in enumerate(self.encoder_rates):
+                p = f"encoder.block.{i}"
+                for r, dil in enumerate((1, 3, 9)):
+                    nxt = P(f"{p}.res_unit{r + 2}.snake1.alpha") if r < 2 else P(p + ".snake1.alpha")
+                    act = self._res_unit_tc(skip, act, f"{p}.res_unit{r + 1}", dil, nxt)
+                # strided conv: input viewed as (B, T/s, s*C); output feeds the next block (or encoder.snake1)
+                nxt = P(f"encoder.block.{i + 1}.res_unit1.snake1.alpha") if i + 1 < nb else P("encoder.snake1.alpha")
+                skip, act = self._tc(act, p + ".conv1", 2 * d, 2 * s, 1, math.ceil(s / 2), T // s, s=s, alpha=nxt,
+                                     alpha_mod=2 * d, out_f32=(i + 1 < nb))
+                d *= 2
+                T //= s
+            z, _ = self._tc(act, "encoder.conv2", self.latent_dim, 3, 1, 1, T, out_f32=True, out_split=False)
+            zq_cl, codes, lat = self.quantizer._rvq(0, in_f=z, channels_last=True)
+        return {"z": zq_cl.permute(0, 2, 1), "codes": codes, "latents": lat, "length": N}
+
+    def _decode_tc(self, z):
+        """z: (B, latent, T) fp32 (the reference's layout) -> audio (B, 1, T*hop)."""
+        P = self.params.get
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            zc = z.permute(0, 2, 1).contiguous()  # channels-last
+            act = self._split(zc)
+            B, T, _ = zc.shape
+            c = self.decoder_dim
+            _, act = self._tc(act, "decoder.conv1", c, 7, 1, 3, T, alpha=P("decoder.block.0.snake1.alpha"), alpha_mod=c)
+            nb = len(self.decoder_rates)
+            for i, s in enumerate(self.decoder_rates):
+                p = f"decoder.block.{i}"
+                co = c // 2
+                pad = math.ceil(s / 2)
+                # transposed conv as ONE GEMM with N = s*Cout phase-major columns and taps (x[q], x[q-1])
+                skip, act = self._tc(act, p + ".conv_t1", s * co, 2, -1, 0, T + 1, alpha=P(p + ".res_unit1.snake1.alpha"),
+                                     alpha_mod=co, out_f32=True, bias_mod=co, out_rows=T * s, out_offset=-pad * co)
+                T *= s
+                for r, dil in enumerate((1, 3, 9)):
+                    if r < 2:
+                        nxt = P(f"{p}.res_unit{r + 2}.snake1.alpha")
+                    else:
+                        nxt = P(f"decoder.block.{i + 1}.snake1.alpha") if i + 1 < nb else P("decoder.snake1.alpha")
+                    act = self._res_unit_tc(skip, act, f"{p}.res_unit{r + 1}", dil, nxt)
+                c = co
+            audio = torch.empty(B, 1, T, device=z.device, dtype=torch.float32)
+            _lib.check(lib.vnb_codec_conv_out(_lib.ptr(act[0]), _lib.ptr(act[1]), _lib.ptr(P("decoder.conv2.weight")),
+                                              _lib.ptr(P("decoder.conv2.bias")), _lib.ptr(audio), B, T, c, 7, 3,
+                                              _lib.stream_ptr(z.device)))
+        return audio
 
     def forward(self, audio_data, sample_rate=None):
         enc = self.encode(audio_data, sample_rate)

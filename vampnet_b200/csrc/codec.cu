@@ -144,6 +144,8 @@ struct RvqArgs {
   const float* cbn;   // (L, V, 8) L2-normalised codebooks (F.normalize, eps 1e-12)
   int64_t* codes; float* zq; float* latents;
   int B, D, T, L, V, mode;
+  int cl;                       // 1: in_f (mode 0) and zq are channels-last (B, T, D) -- tensor-core codec path
+  __nv_bfloat16* zq_hi; __nv_bfloat16* zq_lo;  // optional split-bf16 copy of zq (channels-last only)
 };
 
 __global__ void __launch_bounds__(256) rvq_kernel(const RvqArgs a) {
@@ -162,7 +164,8 @@ __global__ void __launch_bounds__(256) rvq_kernel(const RvqArgs a) {
   if (a.mode == 0) {
     for (int i = threadIdx.x; i < D * RQ_T; i += 256) {
       const int c = i / RQ_T, t = i - c * RQ_T;
-      res[t][c] = t < nt ? a.in_f[(static_cast<size_t>(b) * D + c) * a.T + t0 + t] : 0.f;
+      res[t][c] = t < nt ? (a.cl ? a.in_f[(static_cast<size_t>(b) * a.T + t0 + t) * D + c]
+                               : a.in_f[(static_cast<size_t>(b) * D + c) * a.T + t0 + t]) : 0.f;
     }
   } else {
     for (int i = threadIdx.x; i < D * RQ_T; i += 256) res[i / D][i % D] = 0.f;  // here `res` accumulates zq
@@ -267,16 +270,24 @@ __global__ void __launch_bounds__(256) rvq_kernel(const RvqArgs a) {
   for (int i = threadIdx.x; i < D * RQ_T; i += 256) {
     const int c = i / RQ_T, t = i - c * RQ_T;
     if (t >= nt) continue;
-    const size_t o = (static_cast<size_t>(b) * D + c) * a.T + t0 + t;
-    a.zq[o] = a.mode == 0 ? a.in_f[o] - res[t][c] : res[t][c];
+    const size_t o = a.cl ? (static_cast<size_t>(b) * a.T + t0 + t) * D + c : (static_cast<size_t>(b) * D + c) * a.T + t0 + t;
+    const float v = a.mode == 0 ? a.in_f[o] - res[t][c] : res[t][c];
+    a.zq[o] = v;
+    if (a.zq_hi) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      a.zq_hi[o] = h;
+      a.zq_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
   }
 }
 
 cudaError_t launch_rvq(int mode, const float* in_f, const int64_t* in_codes, const float* win, const float* bin,
                        const float* wout, const float* bout, const float* cb, const float* cbn, int64_t* codes,
-                       float* zq, float* latents, int B, int D, int T, int L, int V, cudaStream_t st) {
+                       float* zq, float* latents, int B, int D, int T, int L, int V, cudaStream_t st, int cl = 0,
+                       void* zq_hi = nullptr, void* zq_lo = nullptr) {
   if (D > RQ_MAXD) return cudaErrorInvalidValue;
-  RvqArgs a{in_f, in_codes, win, bin, wout, bout, cb, cbn, codes, zq, latents, B, D, T, L, V, mode};
+  RvqArgs a{in_f, in_codes, win, bin, wout, bout, cb, cbn, codes, zq, latents, B, D, T, L, V, mode, cl,
+            reinterpret_cast<__nv_bfloat16*>(zq_hi), reinterpret_cast<__nv_bfloat16*>(zq_lo)};
   dim3 grid((T + RQ_T - 1) / RQ_T, B);
   rvq_kernel<<<grid, 256, 0, st>>>(a);
   return cudaGetLastError();
@@ -296,9 +307,10 @@ int32_t vnb_codec_conv1d(const float* x, const float* w, const float* bias, cons
 }
 int32_t vnb_codec_rvq(int32_t mode, const float* in_f, const int64_t* in_codes, const float* win, const float* bin,
                       const float* wout, const float* bout, const float* cb, const float* cbn, int64_t* codes, float* zq,
-                      float* latents, int32_t B, int32_t D, int32_t T, int32_t L, int32_t V, void* stream) {
+                      float* latents, int32_t B, int32_t D, int32_t T, int32_t L, int32_t V, int32_t channels_last,
+                      void* zq_hi, void* zq_lo, void* stream) {
   cudaError_t e = launch_rvq(mode, in_f, in_codes, win, bin, wout, bout, cb, cbn, codes, zq, latents, B, D, T, L, V,
-                             reinterpret_cast<cudaStream_t>(stream));
+                             reinterpret_cast<cudaStream_t>(stream), channels_last, zq_hi, zq_lo);
   return e == cudaSuccess ? 0 : vnb_set_error_cuda("vnb_codec_rvq", static_cast<int>(e));
 }
 }

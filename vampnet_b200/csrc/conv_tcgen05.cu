@@ -1,0 +1,351 @@
+// vampnet_b200 — codec convolutions on the sm_100a tensor cores.
+//
+// A 1-D convolution is a GEMM over (tap, input-channel) with the A operand read at a time shift per tap:
+//   y[b, q, n] = bias[n] + sum_tap sum_ci W[n, tap, ci] * a[b, q*s + tap*dil - pad, ci]
+// Activations are channels-last (B, T, C), so the A tile of k-block (tap, channel block) is a plain TMA box at row
+// q0 + shift; rows outside [0, T) are zero-filled by TMA, which IS the convolution's zero padding.  Strided
+// convolutions view the input as (B, T/s, s*C): x[q*s + e] = view[q + floor(e/s), (e mod s)*C + ci].  A transposed
+// convolution (kernel 2s, stride s) is ONE GEMM with N = s*Cout columns (phase-major) and two taps (x[q], x[q-1]);
+// its (T+1, s*Cout) result is the (T*s, Cout) output shifted by `pad` rows, so the store is row-major plus an
+// offset and a validity mask.  (Architecture: transformers/models/dac/modeling_dac.py:173-268, 405-473; reference
+// call sites vampnet/interface.py:223, vampnet/modules/transformer.py:671-675.)
+//
+// Precision: the codec must stay within 1e-3 of the fp32 reference waveform, which bf16 operands cannot give
+// over ~30 layers.  Operands are therefore SPLIT bf16 pairs (x = hi + lo, 16 mantissa bits together) and every
+// k-step issues three tcgen05.mma (hi*hi + hi*lo + lo*hi) into the same fp32 TMEM accumulator: fp32-grade
+// products at 1/3 of the bf16 tensor rate, still >20x the fp32 CUDA-core rate.
+//
+// Epilogue (fused): + bias, + fp32 skip (residual units), store the fp32 stream, and/or apply the NEXT layer's
+// Snake activation (x + sin^2(alpha x)/alpha) and store it split as hi/lo bf16 = the next conv's A operand.
+//
+// Same warp-specialised structure as gemm_tcgen05.cu: TMA producer warp, single-thread MMA issuer, 4 epilogue
+// warps, double-buffered TMEM accumulators, persistent over tiles of 128 rows x BN columns (BN <= 128, runtime).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vnb {
+
+constexpr int CT_BM = 128, CT_BK = 64, CT_STAGES = 3, CT_MAXBN = 128;
+constexpr int CT_A_BYTES = CT_BM * CT_BK * 2;        // 16 KiB (one of hi / lo)
+constexpr int CT_B_BYTES = CT_MAXBN * CT_BK * 2;     // 16 KiB (one of hi / lo)
+constexpr int CT_STAGE_BYTES = 2 * CT_A_BYTES + 2 * CT_B_BYTES;  // 64 KiB
+constexpr int CT_STG_BYTES = 4 * 32 * 36 * 4;
+constexpr int CT_SMEM = CT_STAGES * CT_STAGE_BYTES + CT_STG_BYTES + 1024 + 256;
+constexpr int CT_THREADS = 256;
+
+struct ConvTcArgs {
+  int Bn, Tq, N, BN;            // batch, output rows per batch item, output columns, column tile
+  int cblocks, taps, dil, pad, s, Cin;
+  const float* bias; int bias_mod;
+  const float* alpha; int alpha_mod;
+  const float* resid;           // fp32, same indexing as out
+  float* out_f32;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  long long out_batch_stride;   // elements
+  long long out_offset;         // elements added to q*N + n (negative for transposed convs)
+  long long out_limit;          // valid flat range per batch item: [0, out_limit)
+  int do_tanh;
+};
+
+__device__ __forceinline__ float snake_act(float v, float a) {
+  const float s = sinf(a * v);
+  return v + s * s / (a + 1e-9f);
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                    const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                    const ConvTcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* stg_all = reinterpret_cast<float*>(smem + CT_STAGES * CT_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CT_STAGES * CT_STAGE_BYTES + CT_STG_BYTES);
+  uint64_t* empty_bar = full_bar + CT_STAGES;
+  uint64_t* tfull_bar = empty_bar + CT_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (g.Tq + CT_BM - 1) / CT_BM;
+  const int n_tiles = (g.N + g.BN - 1) / g.BN;
+  const int num_tiles = g.Bn * m_tiles * n_tiles;
+  const int num_kb = g.taps * g.cblocks;
+  const uint32_t stage_tx = 2 * CT_A_BYTES + 2 * g.BN * CT_BK * 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAh); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < CT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (batch, q0, n0): n fastest so that consecutive CTAs share the same A rows (L2 reuse of activations)
+  auto decode = [&](int tile, int& b, int& q0, int& n0) {
+    n0 = (tile % n_tiles) * g.BN;
+    const int r = tile / n_tiles;
+    q0 = (r % m_tiles) * CT_BM;
+    b = r / m_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int b, q0, n0;
+        decode(tile, b, q0, n0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / g.cblocks, cblk = kb - tap * g.cblocks;
+          const int e = tap * g.dil - g.pad;                     // time shift in input samples
+          const int qs = (e >= 0) ? e / g.s : -((-e + g.s - 1) / g.s);  // floor(e / s)
+          const int r = e - qs * g.s;                            // 0 <= r < s
+          const int col = r * g.Cin + cblk * CT_BK;
+          mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
+          uint8_t* sa = smem + stage * CT_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_3d(sa, &tmAh, &full_bar[stage], col, q0 + qs, b);
+          tma_load_3d(sa + CT_A_BYTES, &tmAl, &full_bar[stage], col, q0 + qs, b);
+          tma_load_2d(sa + 2 * CT_A_BYTES, &tmWh, &full_bar[stage], kb * CT_BK, n0);
+          tma_load_2d(sa + 2 * CT_A_BYTES + CT_B_BYTES, &tmWl, &full_bar[stage], kb * CT_BK, n0);
+          if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(CT_BM, g.BN);
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1, 710 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * CT_MAXBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 720 + stage);
+          tc_fence_after();
+          const uint32_t ah = smem_u32(smem + stage * CT_STAGE_BYTES);
+          const uint32_t al = ah + CT_A_BYTES, wh = ah + 2 * CT_A_BYTES, wl = wh + CT_B_BYTES;
+#pragma unroll
+          for (int k = 0; k < CT_BK / 16; ++k) {
+            const uint64_t dAh = umma_desc_sw128(ah + k * 32), dAl = umma_desc_sw128(al + k * 32);
+            const uint64_t dWh = umma_desc_sw128(wh + k * 32), dWl = umma_desc_sw128(wl + k * 32);
+            umma_bf16(d_tmem, dAh, dWh, idesc, (kb | k) != 0 ? 1u : 0u);  // hi*hi
+            umma_bf16(d_tmem, dAh, dWl, idesc, 1u);                        // hi*lo
+            umma_bf16(d_tmem, dAl, dWh, idesc, 1u);                        // lo*hi
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == CT_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int quad = warp & 3;
+    float* stg = stg_all + quad * (32 * 36);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      int b, q0, n0;
+      decode(tile, b, q0, n0);
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1, 730 + acc);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * CT_MAXBN;
+      const long long bbase = static_cast<long long>(b) * g.out_batch_stride;
+      const int c4 = (lane & 7) * 4;
+      for (int c = 0; c < g.BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(t_addr + c * 32, v);
+        tmem_wait_ld();
+        {  // transpose through smem: lane == row  ->  8 lanes per row, 4 columns each
+          float4* dst = reinterpret_cast<float4*>(stg + lane * 36);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                 __uint_as_float(v[4 * i + 3]));
+          __syncwarp();
+        }
+        const int n = n0 + c * 32 + c4;  // first of this lane's 4 columns
+        if (n < g.N) {
+          const float4 bv = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias + (n % g.bias_mod)))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 al4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.alpha) al4 = __ldg(reinterpret_cast<const float4*>(g.alpha + (n % g.alpha_mod)));
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int r = itr * 4 + (lane >> 3);
+            const int q = q0 + quad * 32 + r;
+            const long long flat = static_cast<long long>(q) * g.N + n + g.out_offset;
+            if (q < g.Tq && flat >= 0 && flat < g.out_limit) {
+              float4 a = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
+              a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+              const long long o = bbase + flat;
+              if (g.resid) {
+                const float4 x = __ldcg(reinterpret_cast<const float4*>(g.resid + o));
+                a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+              }
+              if (g.do_tanh) { a.x = tanhf(a.x); a.y = tanhf(a.y); a.z = tanhf(a.z); a.w = tanhf(a.w); }
+              if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + o) = a;
+              if (g.out_hi) {
+                if (g.alpha) {
+                  a.x = snake_act(a.x, al4.x); a.y = snake_act(a.y, al4.y);
+                  a.z = snake_act(a.z, al4.z); a.w = snake_act(a.w, al4.w);
+                }
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(a.x), h1 = __float2bfloat16_rn(a.y),
+                                    h2 = __float2bfloat16_rn(a.z), h3 = __float2bfloat16_rn(a.w);
+                uint2 hi, lo;
+                hi.x = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+                hi.y = pack_bf16x2(__bfloat162float(h2), __bfloat162float(h3));
+                lo.x = pack_bf16x2(a.x - __bfloat162float(h0), a.y - __bfloat162float(h1));
+                lo.y = pack_bf16x2(a.z - __bfloat162float(h2), a.w - __bfloat162float(h3));
+                *reinterpret_cast<uint2*>(g.out_hi + o) = hi;
+                *reinterpret_cast<uint2*>(g.out_lo + o) = lo;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<256>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Edge layers on CUDA cores (Cin = 1 / Cout = 1: not GEMM shaped, < 0.1 % of the codec's FLOPs).
+// encoder.conv1: x (B, 1, T) fp32 -> y (B, T, C) channels-last; stores the fp32 stream and snake_next(y) split hi/lo.
+__global__ void codec_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                const float* __restrict__ alpha, float* __restrict__ out_f32,
+                                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int B, int T, int C,
+                                int K, int pad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * T * C) return;
+  const int c = static_cast<int>(i % C);
+  const long long bt = i / C;
+  const int t = static_cast<int>(bt % T), b = static_cast<int>(bt / T);
+  float acc = bias[c];
+  for (int k = 0; k < K; ++k) {
+    const int xi = t + k - pad;
+    if (xi >= 0 && xi < T) acc = fmaf(w[c * K + k], x[static_cast<long long>(b) * T + xi], acc);
+  }
+  out_f32[i] = acc;
+  const float a = snake_act(acc, alpha[c]);
+  const __nv_bfloat16 h = __float2bfloat16_rn(a);
+  out_hi[i] = h;
+  out_lo[i] = __float2bfloat16_rn(a - __bfloat162float(h));
+}
+// decoder.conv2: activated input (B, T, C) as hi/lo -> audio (B, 1, T) = tanh(bias + sum_k sum_c w[c, k] * a[t+k-pad, c])
+__global__ void __launch_bounds__(256) codec_out_kernel(const __nv_bfloat16* __restrict__ ah,
+                                                        const __nv_bfloat16* __restrict__ al, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ audio, int B,
+                                                        int T, int C, int K, int pad) {
+  extern __shared__ float sm[];  // [(256 + K - 1)][C] activations + [K][C] weights
+  const int t0 = blockIdx.x * 256, b = blockIdx.y;
+  const int span = 256 + K - 1;
+  float* sa = sm;
+  float* sw = sm + span * C;
+  for (int i = threadIdx.x; i < span * C; i += 256) {
+    const int p = i / C, c = i - p * C;
+    const int t = t0 + p - pad;
+    float v = 0.f;
+    if (t >= 0 && t < T) {
+      const long long o = (static_cast<long long>(b) * T + t) * C + c;
+      v = __bfloat162float(ah[o]) + __bfloat162float(al[o]);
+    }
+    sa[i] = v;
+  }
+  for (int i = threadIdx.x; i < K * C; i += 256) {
+    const int k = i / C, c = i - k * C;
+    sw[i] = w[c * K + k];  // weight (1, C, K)
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= T) return;
+  float acc = bias[0];
+  for (int k = 0; k < K; ++k) {
+    const float* ar = sa + (threadIdx.x + k) * C;
+    const float* wr = sw + k * C;
+    for (int c = 0; c < C; ++c) acc = fmaf(wr[c], ar[c], acc);
+  }
+  audio[static_cast<long long>(b) * T + t] = tanhf(acc);
+}
+
+}  // namespace vnb
+
+using namespace vnb;
+extern "C" {
+
+int32_t vnb_codec_conv_tc(const void* a_hi, const void* a_lo, int32_t B, int32_t Tin, int32_t Cin, int32_t s,
+                          const void* w_hi, const void* w_lo, int32_t N, int32_t taps, int32_t dil, int32_t pad,
+                          int32_t Tq, const float* bias, int32_t bias_mod, const float* alpha, int32_t alpha_mod,
+                          const float* resid, float* out_f32, void* out_hi, void* out_lo, int64_t out_batch_stride,
+                          int64_t out_offset, int64_t out_limit, int32_t do_tanh, void* stream) {
+  if (Tin % s != 0) return vnb_set_error_cuda("vnb_codec_conv_tc: Tin must be a multiple of the stride", 1);
+  if (N % 32 != 0 || Cin % 4 != 0) return vnb_set_error_cuda("vnb_codec_conv_tc: N % 32 and Cin % 4 required", 1);
+  ConvTcArgs g;
+  g.Bn = B; g.Tq = Tq; g.N = N;
+  g.BN = N >= 128 ? 128 : N;         // N in {64, 96, 128, ...}: multiples of 32 up to 128
+  if (N > 128 && N % 128 != 0) g.BN = (N % 96 == 0) ? 96 : 64;
+  g.cblocks = (Cin + CT_BK - 1) / CT_BK; g.taps = taps; g.dil = dil; g.pad = pad; g.s = s; g.Cin = Cin;
+  g.bias = bias; g.bias_mod = bias_mod; g.alpha = alpha; g.alpha_mod = alpha_mod; g.resid = resid; g.out_f32 = out_f32;
+  g.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); g.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  g.out_batch_stride = out_batch_stride; g.out_offset = out_offset; g.out_limit = out_limit; g.do_tanh = do_tanh;
+  const int Ktot = taps * g.cblocks * CT_BK;
+  CUtensorMap tAh, tAl, tWh, tWl;
+  const uint64_t rows = static_cast<uint64_t>(Tin / s), cols = static_cast<uint64_t>(s) * Cin;
+  if (!make_tmap_3d(&tAh, a_hi, B, rows, cols, cols, CT_BM, CT_BK) || !make_tmap_3d(&tAl, a_lo, B, rows, cols, cols, CT_BM, CT_BK) ||
+      !make_tmap_2d(&tWh, w_hi, N, Ktot, g.BN, CT_BK) || !make_tmap_2d(&tWl, w_lo, N, Ktot, g.BN, CT_BK))
+    return vnb_set_error_cuda(tmap_error(), 1);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM);
+    if (e != cudaSuccess) return vnb_set_error_cuda("cudaFuncSetAttribute(conv_tcgen05_kernel)", static_cast<int>(e));
+    attr = true;
+  }
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int tiles = B * ((Tq + CT_BM - 1) / CT_BM) * ((N + g.BN - 1) / g.BN);
+  conv_tcgen05_kernel<<<tiles < sms ? tiles : sms, CT_THREADS, CT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tAh, tAl, tWh, tWl, g);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : vnb_set_error_cuda("conv_tcgen05_kernel launch", static_cast<int>(e));
+}
+
+int32_t vnb_codec_conv_in(const float* x, const float* w, const float* bias, const float* alpha, float* out_f32,
+                          void* out_hi, void* out_lo, int32_t B, int32_t T, int32_t C, int32_t K, int32_t pad,
+                          void* stream) {
+  const long long total = static_cast<long long>(B) * T * C;
+  codec_in_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, w, bias, alpha, out_f32, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), B, T,
+      C, K, pad);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : vnb_set_error_cuda("codec_in_kernel", static_cast<int>(e));
+}
+
+int32_t vnb_codec_conv_out(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* audio, int32_t B,
+                           int32_t T, int32_t C, int32_t K, int32_t pad, void* stream) {
+  const size_t smem = (static_cast<size_t>(256 + K - 1) * C + static_cast<size_t>(K) * C) * sizeof(float);
+  static size_t cur = 48 * 1024;
+  if (smem > cur) {
+    cudaError_t e = cudaFuncSetAttribute(codec_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return vnb_set_error_cuda("cudaFuncSetAttribute(codec_out_kernel)", static_cast<int>(e));
+    cur = smem;
+  }
+  dim3 grid((T + 255) / 256, B);
+  codec_out_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a_hi), reinterpret_cast<const __nv_bfloat16*>(a_lo), w, bias, audio, B, T, C, K,
+      pad);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : vnb_set_error_cuda("codec_out_kernel", static_cast<int>(e));
+}
+}
