@@ -23,7 +23,7 @@ def build(cfg, seed=0, precision="tc"):
     return w, m.to("cuda")
 
 
-SMALL = do.CodecConfig(encoder_dim=16, decoder_dim=128)
+SMALL = do.CodecConfig(encoder_dim=32, decoder_dim=512)  # every width a multiple of 32 (tensor-core tiles)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -95,6 +95,6 @@ def test_full_size_layers(precision):
 
 def test_cpu_codec_raises():
     from vampnet_b200.codec import DAC
-    m = DAC(encoder_dim=16, decoder_dim=128)
+    m = DAC(encoder_dim=32, decoder_dim=512)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.encode(torch.zeros(1, 1, 768))

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 COARSE = dict(n_heads=4, n_layers=2, n_codebooks=4, n_conditioning_codebooks=0, embedding_dim=256)
 C2F = dict(n_heads=4, n_layers=1, n_codebooks=14, n_conditioning_codebooks=4, embedding_dim=256)
-CODEC = do.CodecConfig(encoder_dim=16, decoder_dim=128)
+CODEC = do.CodecConfig(encoder_dim=32, decoder_dim=512)
 GREEDY = dict(sample_cutoff=-1.0, mask_temperature=0.0)
 
 

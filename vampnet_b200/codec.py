@@ -154,6 +154,11 @@ class DAC(nn.Module):
         self.sample_rate = sample_rate
         # "tc": tcgen05 tensor-core convolutions with split-bf16 operands (fp32-grade); "fp32": CUDA-core kernels
         assert precision in ("tc", "fp32")
+        widths = [encoder_dim * 2 ** i for i in range(len(self.encoder_rates) + 1)] + \
+                 [decoder_dim // 2 ** i for i in range(len(self.decoder_rates) + 1)]
+        if precision == "tc" and any(w % 32 for w in widths):
+            raise ValueError(f"precision='tc' needs every channel width to be a multiple of 32, got {widths}; "
+                             "use precision='fp32'")
         self.precision = precision
         self.hop_length = int(math.prod(self.encoder_rates))
         self._cfg = dict(encoder_dim=encoder_dim, encoder_rates=self.encoder_rates, latent_dim=self.latent_dim,
