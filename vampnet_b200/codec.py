@@ -168,12 +168,12 @@ class DAC(nn.Module):
         g = torch.Generator().manual_seed(0)
         for name, shape in _layout(self._cfg).items():
             if name.endswith(".alpha"):
-                t = torch.ones(shape)
+                t = torch.ones(shape, device="cpu")
             elif name.endswith(".bias"):
-                t = torch.zeros(shape)
+                t = torch.zeros(shape, device="cpu")
             else:
                 fan = shape[1] * (shape[2] if len(shape) == 3 else 1)
-                t = torch.randn(shape, generator=g) / math.sqrt(max(fan, 1))
+                t = torch.randn(shape, generator=g, device="cpu") / math.sqrt(max(fan, 1))
             self.params.add(name, t)
         self.quantizer = _Quantizer(self)
         self._pack = None
