@@ -29,9 +29,11 @@ constexpr int CT_BM = 128, CT_BK = 64, CT_STAGES = 3, CT_MAXBN = 128;
 constexpr int CT_A_BYTES = CT_BM * CT_BK * 2;        // 16 KiB (one of hi / lo)
 constexpr int CT_B_BYTES = CT_MAXBN * CT_BK * 2;     // 16 KiB (one of hi / lo)
 constexpr int CT_STAGE_BYTES = 2 * CT_A_BYTES + 2 * CT_B_BYTES;  // 64 KiB
-constexpr int CT_STG_BYTES = 4 * 32 * 36 * 4;
+constexpr int CT_EPI_WARPS = 8;                       // two warps per TMEM lane quadrant (even / odd 32-column chunks)
+constexpr int CT_STG_PITCH = 33;                      // scalar, conflict-free transposes (8 x 32 x 33 floats fit beside the ring)
+constexpr int CT_STG_BYTES = CT_EPI_WARPS * 32 * CT_STG_PITCH * 4;
 constexpr int CT_SMEM = CT_STAGES * CT_STAGE_BYTES + CT_STG_BYTES + 1024 + 256;
-constexpr int CT_THREADS = 256;
+constexpr int CT_THREADS = 128 + 32 * CT_EPI_WARPS;
 
 struct ConvTcArgs {
   int Bn, Tq, N, BN;            // batch, output rows per batch item, output columns, column tile
@@ -47,9 +49,15 @@ struct ConvTcArgs {
   int do_tanh;
 };
 
-__device__ __forceinline__ float snake_act(float v, float a) {
-  const float s = sinf(a * v);
-  return v + s * s / (a + 1e-9f);
+// Snake: v + sin^2(a v) / (a + 1e-9).  sin via two-constant Cody-Waite reduction to [-pi, pi] + MUFU.SIN
+// (abs error < 1e-6 for |a v| < 1e4, far below the split-bf16 product error); 1/(a+1e-9) is passed in.
+__device__ __forceinline__ float snake_act(float v, float a, float inv_a) {
+  const float t = a * v;
+  const float k = rintf(t * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, t);   // 2*pi rounded to fp32
+  r = fmaf(k, 1.7484555e-7f, r);                 // minus the remainder of 2*pi
+  const float s = __sinf(r);
+  return fmaf(s * s, inv_a, v);
 }
 
 __global__ void __launch_bounds__(CT_THREADS, 1)
@@ -77,7 +85,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < CT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], CT_EPI_WARPS); }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc<256>(tmem_slot);
@@ -147,7 +155,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     }
   } else if (warp >= 4) {
     const int quad = warp & 3;
-    float* stg = stg_all + quad * (32 * 36);
+    const int half = (warp - 4) >> 2;  // this warp takes the 32-column chunks with (c & 1) == half
+    float* stg = stg_all + (warp - 4) * (32 * CT_STG_PITCH);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -158,32 +167,32 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * CT_MAXBN;
       const long long bbase = static_cast<long long>(b) * g.out_batch_stride;
       const int c4 = (lane & 7) * 4;
-      for (int c = 0; c < g.BN / 32; ++c) {
+      for (int c = half; c < g.BN / 32; c += 2) {
         uint32_t v[32];
         tmem_ld_x32(t_addr + c * 32, v);
         tmem_wait_ld();
-        {  // transpose through smem: lane == row  ->  8 lanes per row, 4 columns each
-          float4* dst = reinterpret_cast<float4*>(stg + lane * 36);
+        // transpose through smem: lane == row  ->  8 lanes per row, 4 columns each
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                 __uint_as_float(v[4 * i + 3]));
-          __syncwarp();
-        }
+        for (int j = 0; j < 32; ++j) stg[lane * CT_STG_PITCH + j] = __uint_as_float(v[j]);
+        __syncwarp();
         const int n = n0 + c * 32 + c4;  // first of this lane's 4 columns
         if (n < g.N) {
           const float4 bv = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias + (n % g.bias_mod)))
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 al4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g.alpha) al4 = __ldg(reinterpret_cast<const float4*>(g.alpha + (n % g.alpha_mod)));
+          float4 al4 = make_float4(1.f, 1.f, 1.f, 1.f), ia4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (g.alpha) {
+            al4 = __ldg(reinterpret_cast<const float4*>(g.alpha + (n % g.alpha_mod)));
+            ia4 = make_float4(1.0f / (al4.x + 1e-9f), 1.0f / (al4.y + 1e-9f), 1.0f / (al4.z + 1e-9f),
+                              1.0f / (al4.w + 1e-9f));
+          }
 #pragma unroll
           for (int itr = 0; itr < 8; ++itr) {
             const int r = itr * 4 + (lane >> 3);
             const int q = q0 + quad * 32 + r;
             const long long flat = static_cast<long long>(q) * g.N + n + g.out_offset;
             if (q < g.Tq && flat >= 0 && flat < g.out_limit) {
-              float4 a = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
-              a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+              const float* sp = stg + r * CT_STG_PITCH + c4;
+              float4 a = make_float4(sp[0] + bv.x, sp[1] + bv.y, sp[2] + bv.z, sp[3] + bv.w);
               const long long o = bbase + flat;
               if (g.resid) {
                 const float4 x = __ldcg(reinterpret_cast<const float4*>(g.resid + o));
@@ -193,16 +202,16 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
               if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + o) = a;
               if (g.out_hi) {
                 if (g.alpha) {
-                  a.x = snake_act(a.x, al4.x); a.y = snake_act(a.y, al4.y);
-                  a.z = snake_act(a.z, al4.z); a.w = snake_act(a.w, al4.w);
+                  a.x = snake_act(a.x, al4.x, ia4.x); a.y = snake_act(a.y, al4.y, ia4.y);
+                  a.z = snake_act(a.z, al4.z, ia4.z); a.w = snake_act(a.w, al4.w, ia4.w);
                 }
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(a.x), h1 = __float2bfloat16_rn(a.y),
-                                    h2 = __float2bfloat16_rn(a.z), h3 = __float2bfloat16_rn(a.w);
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(a.x, a.y), h23 = __floats2bfloat162_rn(a.z, a.w);
+                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
                 uint2 hi, lo;
-                hi.x = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
-                hi.y = pack_bf16x2(__bfloat162float(h2), __bfloat162float(h3));
-                lo.x = pack_bf16x2(a.x - __bfloat162float(h0), a.y - __bfloat162float(h1));
-                lo.y = pack_bf16x2(a.z - __bfloat162float(h2), a.w - __bfloat162float(h3));
+                hi.x = *reinterpret_cast<const uint32_t*>(&h01);
+                hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+                lo.x = pack_bf16x2(a.x - f01.x, a.y - f01.y);
+                lo.y = pack_bf16x2(a.z - f23.x, a.w - f23.y);
                 *reinterpret_cast<uint2*>(g.out_hi + o) = hi;
                 *reinterpret_cast<uint2*>(g.out_lo + o) = lo;
               }
@@ -239,7 +248,7 @@ __global__ void codec_in_kernel(const float* __restrict__ x, const float* __rest
     if (xi >= 0 && xi < T) acc = fmaf(w[c * K + k], x[static_cast<long long>(b) * T + xi], acc);
   }
   out_f32[i] = acc;
-  const float a = snake_act(acc, alpha[c]);
+  const float a = snake_act(acc, alpha[c], 1.0f / (alpha[c] + 1e-9f));
   const __nv_bfloat16 h = __float2bfloat16_rn(a);
   out_hi[i] = h;
   out_lo[i] = __float2bfloat16_rn(a - __bfloat162float(h));
@@ -249,33 +258,30 @@ __global__ void __launch_bounds__(256) codec_out_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ al, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ audio, int B,
                                                         int T, int C, int K, int pad) {
-  extern __shared__ float sm[];  // [(256 + K - 1)][C] activations + [K][C] weights
+  extern __shared__ float sm[];  // activations [C][span] (time contiguous: conflict-free across lanes) + weights [C][K]
   const int t0 = blockIdx.x * 256, b = blockIdx.y;
   const int span = 256 + K - 1;
   float* sa = sm;
-  float* sw = sm + span * C;
+  float* sw = sm + C * span;
   for (int i = threadIdx.x; i < span * C; i += 256) {
-    const int p = i / C, c = i - p * C;
+    const int p = i / C, c = i - p * C;  // global reads stay channel-contiguous
     const int t = t0 + p - pad;
     float v = 0.f;
     if (t >= 0 && t < T) {
       const long long o = (static_cast<long long>(b) * T + t) * C + c;
       v = __bfloat162float(ah[o]) + __bfloat162float(al[o]);
     }
-    sa[i] = v;
+    sa[c * span + p] = v;
   }
-  for (int i = threadIdx.x; i < K * C; i += 256) {
-    const int k = i / C, c = i - k * C;
-    sw[i] = w[c * K + k];  // weight (1, C, K)
-  }
+  for (int i = threadIdx.x; i < K * C; i += 256) sw[i] = w[i];  // weight (1, C, K) -> [c][k]
   __syncthreads();
   const int t = t0 + threadIdx.x;
   if (t >= T) return;
   float acc = bias[0];
-  for (int k = 0; k < K; ++k) {
-    const float* ar = sa + (threadIdx.x + k) * C;
-    const float* wr = sw + k * C;
-    for (int c = 0; c < C; ++c) acc = fmaf(wr[c], ar[c], acc);
+  for (int c = 0; c < C; ++c) {
+    const float* ar = sa + c * span + threadIdx.x;
+    const float* wr = sw + c * K;
+    for (int k = 0; k < K; ++k) acc = fmaf(wr[k], ar[k], acc);
   }
   audio[static_cast<long long>(b) * T + t] = tanhf(acc);
 }
