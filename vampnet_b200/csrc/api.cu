@@ -191,7 +191,7 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   const size_t M = ws->M;
   CK(ws->x.alloc(M * d * 4));
   CK(ws->y.alloc(M * d * 2));  // bf16 copy of the residual stream (A operand of QKV / FFN-up / classifier)
-  ws->ss_parts = d / 256;     // one partial row-sum-of-squares per 256-column tile of the producing GEMM
+  ws->ss_parts = 2 * (d / 256);  // two partial row-sums-of-squares (even / odd chunks) per 256-column tile of the producing GEMM
   CK(ws->ssA.alloc(M * ws->ss_parts * 4, true));
   CK(ws->ssB.alloc(M * ws->ss_parts * 4, true));
   CK(ws->qk.alloc(M * 2 * d * 2));

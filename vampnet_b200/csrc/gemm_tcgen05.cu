@@ -25,9 +25,14 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_STG_BYTES = 4 * 32 * 36 * 4;  // epilogue staging: 4 warps x (32 rows x 36 floats)
+constexpr int GEMM_STG_BYTES = 8 * 32 * 36 * 4 - 3072;  // epilogue staging: 4 warps x 32x36 floats, or 8 warps x 32x33 (RESID)
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + GEMM_STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 256;
+// The residual epilogue is bound by memory-level parallelism (residual rows must be fetched before they can be
+// updated): it gets 8 epilogue warps, two per TMEM lane quadrant, splitting the 32-column chunks even / odd.
+template <int EPI> constexpr int gemm_epi_warps() { return EPI == VNB_EPI_RESID ? 8 : 4; }
+template <int EPI> constexpr int gemm_threads() { return 128 + 32 * gemm_epi_warps<EPI>(); }
+constexpr int STG_PITCH_RESID = 33;  // scalar, conflict-free; 8 x 32 x 33 floats fit beside the 4-stage ring
 
 struct GemmArgs {
   int M, N, K;
@@ -68,6 +73,11 @@ __device__ __forceinline__ void stage_rows(float* stg, int lane, const float (&v
   for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   __syncwarp();
 }
+__device__ __forceinline__ void stage_rows33(float* stg, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stg[lane * STG_PITCH_RESID + j] = v[j];
+  __syncwarp();
+}
 
 // fp32 destinations: lane -> (row = it*4 + lane/8, 4 columns at (lane%8)*4).
 // The addend (residual rows or bias) is fetched by prefetch_addend() BEFORE the accumulator chunk is pulled
@@ -90,7 +100,7 @@ __device__ __forceinline__ void prefetch_addend(const GemmArgs& g, int lane, int
     for (int it = 0; it < 8; ++it) add[it] = b4;
   }
 }
-template <bool FUSED>
+template <bool FUSED, int PITCH>
 __device__ __forceinline__ void drain_f32(const GemmArgs& g, const float* stg, int lane, int row_base, int col0,
                                           const float4 (&add)[8], float (&ssacc)[8]) {
   const int c4 = (lane & 7) * 4;
@@ -99,7 +109,8 @@ __device__ __forceinline__ void drain_f32(const GemmArgs& g, const float* stg, i
   const size_t step = static_cast<size_t>(4) * g.N;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    float4 a = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * STG_PITCH + c4);
+    const float* sp = stg + (it * 4 + (lane >> 3)) * PITCH + c4;
+    float4 a = make_float4(sp[0], sp[1], sp[2], sp[3]);
     a.x += add[it].x; a.y += add[it].y; a.z += add[it].z; a.w += add[it].w;
     if (r0 + it * 4 < g.M) {
       *reinterpret_cast<float4*>(base + it * step) = a;
@@ -138,7 +149,7 @@ __device__ __forceinline__ void drain_bf16(__nv_bfloat16* out, int pitch, int M,
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -169,7 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one elected lane of each of the 4 epilogue warps
+      mbar_init(&tempty_bar[a], gemm_epi_warps<EPI>());  // one elected lane of each epilogue warp
     }
     mbar_fence_init();
   }
@@ -244,7 +255,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         b_idx = row / g.T;
         t_idx = row - b_idx * g.T;
       }
-      float* stg = stg_all + quad * STG_FLOATS_PER_WARP;
+      constexpr bool kWide = gemm_epi_warps<EPI>() == 8;
+      const int half = kWide ? ((warp - 4) >> 2) : 0;  // 8-warp epilogue: this warp takes chunks with (c & 1) == half
+      float* stg = kWide ? stg_all + (warp - 4) * (32 * STG_PITCH_RESID) : stg_all + quad * STG_FLOATS_PER_WARP;
       const int row_base = m0 + quad * 32;
       float rs = 1.0f;  // fused RMSNorm of the A operand: rsqrt(mean(x^2) + eps) of this thread's row
       if (g.ss_in != nullptr && row_ok) {
@@ -253,7 +266,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         rs = rsqrtf(t * g.inv_d + g.eps);
       }
       float4 pre0[8];  // residual / bias of the first chunk: fetched while the mainloop of this tile still runs
-      if constexpr (EPI == VNB_EPI_RESID || EPI == VNB_EPI_BIAS_F32) prefetch_addend<EPI>(g, lane, row_base, n0, pre0);
+      if constexpr (EPI == VNB_EPI_RESID || EPI == VNB_EPI_BIAS_F32)
+        prefetch_addend<EPI>(g, lane, row_base, n0 + (gemm_epi_warps<EPI>() == 8 ? ((warp - 4) >> 2) : 0) * 32, pre0);
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
@@ -274,6 +288,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // software-pipelined: the residual rows of chunk c+1 are in flight while chunk c is pulled out of TMEM,
         // transposed and stored (the global-load latency would otherwise be paid 8 times per tile, serially)
         const bool fused_out = (EPI == VNB_EPI_RESID) && g.out_bf16 != nullptr;
+        constexpr int CSTEP = kWide ? 2 : 1;  // chunks owned by this warp: half, half + CSTEP, ...
         float ssacc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) ssacc[i] = 0.f;
@@ -284,22 +299,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float r[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]) * rs;  // rs == 1 unless a norm is fused in
-          stage_rows(stg, lane, r);
-          if (fused_out) drain_f32<true>(g, stg, lane, row_base, n0 + c * 32, add, ssacc);
-          else drain_f32<false>(g, stg, lane, row_base, n0 + c * 32, add, ssacc);
+          if constexpr (kWide) {
+            stage_rows33(stg, lane, r);
+            if (fused_out) drain_f32<true, STG_PITCH_RESID>(g, stg, lane, row_base, n0 + c * 32, add, ssacc);
+            else drain_f32<false, STG_PITCH_RESID>(g, stg, lane, row_base, n0 + c * 32, add, ssacc);
+          } else {
+            stage_rows(stg, lane, r);
+            if (fused_out) drain_f32<true, STG_PITCH>(g, stg, lane, row_base, n0 + c * 32, add, ssacc);
+            else drain_f32<false, STG_PITCH>(g, stg, lane, row_base, n0 + c * 32, add, ssacc);
+          }
         };
         float4 addA[8], addB[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) addA[i] = pre0[i];
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; c += 2) {
-          prefetch_addend<EPI>(g, lane, row_base, n0 + (c + 1) * 32, addB);
+        for (int c = half; c < BN / 32; c += 2 * CSTEP) {
+          prefetch_addend<EPI>(g, lane, row_base, n0 + (c + CSTEP) * 32, addB);
           process(c, addA);
-          if (c + 2 < BN / 32) prefetch_addend<EPI>(g, lane, row_base, n0 + (c + 2) * 32, addA);
-          process(c + 1, addB);
+          if (c + 2 * CSTEP < BN / 32) prefetch_addend<EPI>(g, lane, row_base, n0 + (c + 2 * CSTEP) * 32, addA);
+          process(c + CSTEP, addB);
         }
         if (fused_out) {
-          // per-row sum of squares over this tile's 256 columns: 8 lanes share a row; fixed reduction order
+          // per-row sum of squares over this warp's columns of the tile: 8 lanes share a row; fixed reduction order
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             float v = ssacc[it];
@@ -307,7 +328,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             const int rr = row_base + it * 4 + (lane >> 3);
-            if ((lane & 7) == 0 && rr < g.M) g.ss_out[static_cast<size_t>(n0 / BN) * g.M + rr] = v;
+            const int part = (n0 / BN) * (kWide ? 2 : 1) + half;
+            if ((lane & 7) == 0 && rr < g.M) g.ss_out[static_cast<size_t>(part) * g.M + rr] = v;
           }
         }
       } else {
@@ -373,7 +395,7 @@ static cudaError_t launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, co
   }
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, g);
+  gemm_tcgen05_kernel<EPI><<<grid, gemm_threads<EPI>(), GEMM_SMEM, st>>>(tmA, tmB, g);
   return cudaGetLastError();
 }
 
