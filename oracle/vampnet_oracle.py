@@ -306,11 +306,18 @@ class OracleVampNet:
         elif rng == "torch":
             token = probs.view(-1, V).multinomial(1).squeeze(1).view(B, S)
         else:
-            u = philox.uniform_bsv(philox_key, step, B, S, V)  # (B, S, V) fp32 in (0,1)
-            gmb = -np.log(-np.log(u, dtype=np.float32), dtype=np.float32)
+            # the CUDA sampler's draw: inverse CDF in natural vocabulary order with ONE uniform per row,
+            # token = first v with cumsum(exp(x*inv_t - max))[v] > u * sum  (same distribution as multinomial)
+            u = philox.uniform_bs(philox_key, step, B, S, stream=0)  # (B, S) fp32 in (0,1)
             inv_t = np.float32(1.0 / temperature) if temperature > 0 else np.float32(1.0)
-            score = logits.numpy().astype(np.float32) * inv_t + gmb
-            token = torch.from_numpy(score.argmax(-1).astype(np.int64))
+            xs = logits.numpy().astype(np.float32) * inv_t
+            e = np.exp(xs - xs.max(-1, keepdims=True), dtype=np.float32)
+            cdf = np.cumsum(e, axis=-1, dtype=np.float32)
+            target = u * cdf[..., -1]
+            idx = (cdf > target[..., None]).argmax(-1)
+            none = ~(cdf > target[..., None]).any(-1)
+            idx = np.where(none, logits.numpy().argmax(-1), idx)
+            token = torch.from_numpy(idx.astype(np.int64))
         token_probs = probs.take_along_dim(token.unsqueeze(-1), dim=-1).squeeze(-1)
         return token, token_probs
 

@@ -133,6 +133,7 @@ struct GraphKey {  // graphs bake pointers, so generate() stages z/mask/out in w
 
 struct Workspace {
   int B = 0, T = 0, Tpad = 0, M = 0;
+  unsigned long long last_use = 0;
   DevBuf x, y, qk, vT, att, h, logits, zcur, zorig, tokens, conf, n0, dyn, z_in, mask_in, z_out, ssA, ssB;
   int ss_parts = 0;
   std::vector<GemmPlan> qkv, wo, up, down;
@@ -176,6 +177,8 @@ struct vnb_model {
   std::map<std::pair<int, int>, std::unique_ptr<vnb::Workspace>> ws;
   vnb::Workspace* last = nullptr;
   static constexpr int kMaxSteps = 256;
+  static constexpr size_t kMaxWorkspaces = 6;
+  unsigned long long use_clock = 0;
 };
 
 namespace vnb {
@@ -183,7 +186,17 @@ namespace vnb {
 static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   auto key = std::make_pair(B, T);
   auto it = m->ws.find(key);
-  if (it != m->ws.end()) { *out = it->second.get(); return 0; }
+  if (it != m->ws.end()) { it->second->last_use = ++m->use_clock; *out = it->second.get(); return 0; }
+  // bound the number of live (B, T) workspaces (each holds activations, logits and captured graphs): evict the
+  // least recently used one.  cudaFree synchronises the device, so nothing in flight can still touch it.
+  while (m->ws.size() >= vnb_model::kMaxWorkspaces) {
+    auto lru = m->ws.begin();
+    for (auto i = m->ws.begin(); i != m->ws.end(); ++i)
+      if (i->second->last_use < lru->second->last_use) lru = i;
+    if (m->last == lru->second.get()) m->last = nullptr;
+    cudaDeviceSynchronize();
+    m->ws.erase(lru);
+  }
   const vnb_config& c = m->cfg;
   const int d = c.d_model, L = c.n_layers, Cp = c.n_codebooks - c.n_conditioning_codebooks;
   auto ws = std::make_unique<Workspace>();
@@ -239,6 +252,7 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   consumer(ws->cls, ws->ssA);
   if (!make_attn_plan(&ws->attn, ws->qk.p, ws->vT.p, ws->att.p, m->w.rel_bias, m->w.rel_sat, B, T, ws->Tpad, c.n_heads))
     return fail("plan attention: %s", tmap_error());
+  ws->last_use = ++m->use_clock;
   *out = ws.get();
   m->ws[key] = std::move(ws);
   return 0;

@@ -5,8 +5,8 @@
 //
 // Two kernels, both HBM-bound:
 //   sample_rows_kernel   one warp per (batch, position): reads the 1024 logits of a STILL-MASKED
-//                        position once (32 per lane, float4), warp-shuffle max / sum-exp / Gumbel-max
-//                        arg-max with counter-based Philox noise, writes token + confidence.
+//                        position once (32 per lane, float4), warp-shuffle max / sum-exp, categorical draw by
+//                        inverse CDF with ONE counter-based Philox uniform per row, writes token + confidence.
 //                        Known positions cost 4 bytes.  Algorithmic bytes: V*4 per masked position.
 //   remask_kernel        one CTA per batch row: exact k-th order statistic of the S confidences by a
 //                        4-pass radix select (what sort()[k] yields in the reference), then
@@ -128,33 +128,17 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const SampleStatic a, 
     }
   }
   // arg-max of the raw logits (greedy) or of logits*inv_t + Gumbel (sampling), lowest index on ties
+  // greedy arg-max of the raw logits, lowest index on ties (torch.argmax) -- also the fallback of the sampler
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  if (dyn.do_sample) {
 #pragma unroll
-    for (int i = 0; i < MAXV4; ++i) {
-      if (i < n4) {
-        const uint32_t i4 = i * 32 + lane;
-        uint32_t r[4];
-        philox4x32_10(i4, static_cast<uint32_t>(row), static_cast<uint32_t>(dyn.step), 0u, dyn.seed_lo, dyn.seed_hi, r);
-        const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+  for (int i = 0; i < MAXV4; ++i) {
+    if (i < n4) {
+      const int i4 = i * 32 + lane;
+      const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float sc = __fadd_rn(__fmul_rn(xs[j], dyn.inv_temp), gumbel(u01(r[j])));
-          if (sc > best) { best = sc; best_i = static_cast<int>(i4 * 4 + j); }
-        }
-      }
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < MAXV4; ++i) {
-      if (i < n4) {
-        const int i4 = i * 32 + lane;
-        const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (xs[j] > best) { best = xs[j]; best_i = i4 * 4 + j; }
-      }
+      for (int j = 0; j < 4; ++j)
+        if (xs[j] > best) { best = xs[j]; best_i = i4 * 4 + j; }
     }
   }
 #pragma unroll
@@ -163,24 +147,81 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const SampleStatic a, 
     const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
     if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
   }
-  // softmax probability of the chosen token: probs = softmax(logits * inv_t) (transformer.py:1019-1023)
   mx = warp_max(mx);
   const float m = __fmul_rn(mx, dyn.inv_temp);  // inv_t > 0 so the max commutes
-  float se = 0.f, xt = 0.f;
+  // un-normalised probabilities e_v = exp(x_v * inv_t - m); lane `l` holds v = i*128 + l*4 + j: consecutive
+  // vocabulary entries, so a categorical draw by inverse CDF in natural vocabulary order needs only one prefix
+  // scan per 128-entry chunk.  torch.multinomial (transformer.py:1025) draws from the same distribution.
+  float e[MAXV4][4], csum[MAXV4];
+  float se = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV4; ++i) {
+    csum[i] = 0.f;
+    if (i < n4) {
+      const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+      float ls = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        e[i][j] = expf(__fmul_rn(xs[j], dyn.inv_temp) - m);
+        ls += e[i][j];
+      }
+      csum[i] = ls;                 // this lane's 4 entries of chunk i
+      se += warp_sum(ls);           // chunk totals added in chunk order
+    }
+  }
+  if (dyn.do_sample) {
+    uint32_t r[4];
+    philox4x32_10(static_cast<uint32_t>(s), static_cast<uint32_t>(b), static_cast<uint32_t>(dyn.step), 0u, dyn.seed_lo,
+                  dyn.seed_hi, r);
+    const float target = u01(r[0]) * se;  // token = first v with cumsum(e)[v] > target
+    float base = 0.f;
+    int pick = -1;
+#pragma unroll
+    for (int i = 0; i < MAXV4; ++i) {
+      if (i < n4 && pick < 0) {
+        const float tot = warp_sum(csum[i]);
+        if (base + tot > target) {
+          // inclusive scan of the lane sums of this chunk (Hillis-Steele)
+          float inc = csum[i];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          const float before = base + (inc - csum[i]);
+          int cand = 0x7fffffff;
+          if (base + inc > target) {  // the crossing is at or before this lane's last entry
+            float run = before;
+            int last_pos = -1;  // last entry of this lane with non-zero mass (never pick a filtered-out token)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              run += e[i][j];
+              if (e[i][j] > 0.f) last_pos = j;
+              if (run > target && cand == 0x7fffffff) cand = (i * 32 + lane) * 4 + j;
+            }
+            if (cand == 0x7fffffff && last_pos >= 0) cand = (i * 32 + lane) * 4 + last_pos;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+          pick = cand;
+        }
+        base += tot;
+      }
+    }
+    if (pick >= 0 && pick < V) best_i = pick;  // else (rounding left target >= total): keep the arg-max
+  }
+  // softmax probability of the chosen token: probs = softmax(logits * inv_t) (transformer.py:1019-1023)
+  float xt = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV4; ++i) {
     if (i < n4) {
       const int i4 = i * 32 + lane;
       const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float sx = __fmul_rn(xs[j], dyn.inv_temp);
-        se += expf(sx - m);
-        if (i4 * 4 + j == best_i) xt = sx;
-      }
+      for (int j = 0; j < 4; ++j)
+        if (i4 * 4 + j == best_i) xt = __fmul_rn(xs[j], dyn.inv_temp);
     }
   }
-  se = warp_sum(se);
   xt = warp_sum(xt);  // exactly one lane contributed
   if (lane == 0) {
     const float p = expf(xt - m) / se;
