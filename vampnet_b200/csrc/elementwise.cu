@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ 
                                                     const float* __restrict__ bias, float* __restrict__ x, int M, int T,
                                                     int C, int V1, int K, int d, __nv_bfloat16* __restrict__ xb,
                                                     float* __restrict__ ss, int ss_parts) {
-  __shared__ float lat[EMB_ROWS][EMB_MAXK];
+  __shared__ __align__(16) float lat[EMB_ROWS][EMB_MAXK];
   __shared__ float red[8][EMB_ROWS];
   const int m0 = blockIdx.x * EMB_ROWS;
   for (int i = threadIdx.x; i < EMB_ROWS * K; i += blockDim.x) {
@@ -93,10 +93,17 @@ __global__ void __launch_bounds__(256) embed_kernel(const int32_t* __restrict__ 
     const float bn = bias[n];
 #pragma unroll
     for (int r = 0; r < EMB_ROWS; ++r) acc[r] = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const float wv = __ldg(wt + static_cast<size_t>(k) * d + n);
+    for (int k = 0; k < K; k += 4) {  // K = 8*C is a multiple of 4: one LDS.128 feeds four FMAs per row
+      const float w0 = __ldg(wt + static_cast<size_t>(k) * d + n), w1 = __ldg(wt + static_cast<size_t>(k + 1) * d + n);
+      const float w2 = __ldg(wt + static_cast<size_t>(k + 2) * d + n), w3 = __ldg(wt + static_cast<size_t>(k + 3) * d + n);
 #pragma unroll
-      for (int r = 0; r < EMB_ROWS; ++r) acc[r] = fmaf(wv, lat[r][k], acc[r]);
+      for (int r = 0; r < EMB_ROWS; ++r) {
+        const float4 l = *reinterpret_cast<const float4*>(&lat[r][k]);
+        acc[r] = fmaf(w0, l.x, acc[r]);
+        acc[r] = fmaf(w1, l.y, acc[r]);
+        acc[r] = fmaf(w2, l.z, acc[r]);
+        acc[r] = fmaf(w3, l.w, acc[r]);
+      }
     }
 #pragma unroll
     for (int r = 0; r < EMB_ROWS; ++r) {
