@@ -58,6 +58,42 @@ def family_flops(cfg, T, B, steps):
     return {k: v * steps for k, v in per.items()}
 
 
+def gemm_algorithmic_bytes(B, T, d=1280):
+    """Mean algorithmic HBM bytes of one GEMM launch of a layer (qkv, attn-out, ffn-up, ffn-down weighted 1:1:1:1):
+    A + W + outputs read/written once (bf16 = 2 B, fp32 residual = 4 B read + 4 B written + 2 B bf16 copy)."""
+    M = B * T
+    qkv = M * d * 2 + 3 * d * d * 2 + M * 3 * d * 2
+    out = M * d * 2 + d * d * 2 + M * d * (4 + 4 + 2)
+    up = M * d * 2 + 4 * d * d * 2 + M * 2 * d * 2
+    down = M * 2 * d * 2 + 2 * d * d * 2 + M * d * (4 + 4 + 2)
+    return (qkv + out + up + down) / 4.0
+
+
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch from the committed `ncu --set full` summary
+    (profiles/ncu_gemm_r1_final.txt: one layer's qkv / attn-out / ffn-up / ffn-down at the bench shape)."""
+    path = os.path.join(ROOT, "profiles", "ncu_gemm_r1_final.txt")
+    try:
+        per_kind, cur = {}, None
+        for line in open(path):
+            if line.startswith("== "):
+                cur = line.split("gemm_tcgen05_kernel<")[1][0] if "gemm_tcgen05_kernel<" in line else None
+                if cur is not None:
+                    per_kind.setdefault(cur, []).append(0.0)
+            elif cur is not None and ("dram__bytes_read.sum " in line or "dram__bytes_write.sum " in line):
+                f = line.split()
+                val, unit = float(f[1]), f[2].lower()
+                per_kind[cur][-1] += val * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+        # <1> qkv, <2> residual epilogue (attn-out and ffn-down alternate), <3> ffn-up: weight 1 : 2 : 1
+        if not all(k in per_kind for k in "123"):
+            return None, "profiles/ncu_gemm_r1_final.txt incomplete"
+        mean = lambda v: sum(v) / len(v)
+        return (mean(per_kind["1"]) + 2 * mean(per_kind["2"]) + mean(per_kind["3"])) / 4.0, \
+            "profiles/ncu_gemm_r1_final.txt (ncu --set full, B=32 T=768 coarse layer)"
+    except Exception as e:  # the summary is evidence, not a dependency
+        return None, f"unavailable: {e}"
+
+
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -345,12 +381,14 @@ def main():
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)  # kernel timed inside a long step -> sustained figure
+    traffic, traffic_note = ncu_traffic_per_launch()
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {
         "kernel": "gemm_tcgen05_kernel (all epilogues: qkv, attn-out+residual, ffn-up+GEGLU, ffn-down+residual, classifier+bias)",
         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
-        "traffic": None,
+        "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write)", "traffic_source": traffic_note,
+        "algorithmic_bytes_per_launch": gemm_algorithmic_bytes(B, T) ,
         "flops_per_launch": gemm_fl / max(gemm_n, 1), "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
         "share_of_step": gemm_ms / prof_total if prof_total else None,
         "breakdown_ms": {k: round(fam_ms[k], 3) for k in _lib.FAMILIES},
