@@ -211,7 +211,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_ld_x32(tmem_S + (j & 1) * 64 + half * 32 + lane_off, sr);
       tmem_wait_ld();
       // scale + bias (+ mask of keys beyond T), all in the log2 domain
-      const int rel_lo = k0 - (q0 + AQ - 1), rel_hi = k0 + 31 - q0;
+      // key - query range of THIS WARP's 32 rows x 32 keys: beyond +-sat the bias is one constant
+      const int qw = q0 + quad * 32;
+      const int rel_lo = k0 - (qw + 31), rel_hi = k0 + 31 - qw;
       const bool is_const = (rel_lo >= sat) || (rel_hi <= -sat);
       const bool tail = k0 + 32 > a.T;
       const float bconst = rel_lo >= sat ? bias_hi : bias_lo;

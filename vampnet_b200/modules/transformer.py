@@ -296,7 +296,14 @@ class VampNet(nn.Module):
         # channel r = p*Cp + c  ->  row c*V + p, so a row-major (M, Cp*V) store IS (B, S = t*Cp + c, V)
         p["wcls"] = w.view(V, Cp, d).permute(1, 0, 2).reshape(Cp * V, d).to(bf).contiguous()
         p["bcls"] = wn.bias.float().view(V, Cp).t().reshape(-1).contiguous()
-        rel = torch.arange(-REL_SAT, REL_SAT + 1)
+        # Toeplitz bias table over key-query in [-sat, sat]; sat = the distance beyond which the bucket no longer
+        # changes (91 for the reference's 32 buckets / max_distance 128), found from the bucket function itself
+        probe = relative_position_bucket(torch.arange(-REL_SAT, REL_SAT + 1))
+        sat = REL_SAT
+        while sat > 1 and probe[REL_SAT + sat - 1] == probe[-1] and probe[REL_SAT - (sat - 1)] == probe[0]:
+            sat -= 1
+        self._rel_sat = sat
+        rel = torch.arange(-sat, sat + 1)
         buckets = relative_position_bucket(rel).to(dev)
         p["rel_bias"] = lay[0].self_attn.relative_attention_bias.weight.float()[buckets].contiguous()  # (2*sat+1, H)
         return p
@@ -318,7 +325,7 @@ class VampNet(nn.Module):
             for name in ("emb_table", "emb_wt", "emb_b", "norm1", "wqkv", "wo", "norm3", "w1", "w2", "norm_f", "wcls",
                          "bcls", "rel_bias"):
                 setattr(w, name, p[name].data_ptr())
-            w.rel_sat = REL_SAT
+            w.rel_sat = self._rel_sat
             h = C.c_void_p()
             torch.cuda.synchronize(self.device)
             _lib.check(lib.vnb_model_create(C.byref(cfg), C.byref(w), C.byref(h)))
