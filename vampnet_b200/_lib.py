@@ -86,9 +86,14 @@ def lib():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise RuntimeError(
-            f"{LIB_PATH} not found: build it with `python -m vampnet_b200.build` (nvcc, sm_100a). "
-            "vampnet_b200 has no CPU or PyTorch fallback.")
+        # not a fallback: the only way to get the kernels is to compile them (nvcc cross-compiles sm_100a anywhere)
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:
+            raise RuntimeError(
+                f"{LIB_PATH} not found and building it failed ({e}); build it with `python -m vampnet_b200.build` "
+                "(nvcc, sm_100a). vampnet_b200 has no CPU or PyTorch fallback.") from e
     L = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGS.items():
         fn = getattr(L, name)
