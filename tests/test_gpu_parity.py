@@ -232,3 +232,54 @@ def test_sampler_distribution_chi_square():
     # the reported probability is softmax(logits / T)[token]
     got_p = torch.exp(conf.cpu().flatten().double())
     assert torch.allclose(got_p, p[tokens.cpu().flatten().long()], rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("case", ["default_mask", "mask_2d", "nothing_masked", "everything_masked", "tiny_T", "one_step"])
+def test_generate_edge_cases_vs_oracle(case):
+    """Edge cases of VampNet.generate (reference transformer.py:749-753, 766, 906-913): default mask, 2-D mask,
+    N0 == 0, fully masked input, sequences shorter than any tile, a single sampling step."""
+    cfgd = TINY_C2F if case in ("default_mask", "mask_2d") else TINY_COARSE
+    cfg, sd, model, cb, codec = build(cfgd)
+    orc = vo.OracleVampNet(cfg, sd, "bf16")
+    g = torch.Generator().manual_seed(21)
+    B, T, steps = 2, 29, 4
+    if case == "tiny_T":
+        T = 3
+    if case == "one_step":
+        steps = 1
+    z = torch.randint(0, 1024, (B, cfg.n_codebooks, T), generator=g)
+    if case == "default_mask":
+        mask = None
+    elif case == "mask_2d":
+        mask = torch.ones(B, T, dtype=torch.long)
+        mask[:, ::4] = 0
+    elif case == "nothing_masked":
+        mask = torch.zeros_like(z)
+    elif case == "everything_masked":
+        mask = torch.ones_like(z)
+    else:
+        mask = torch.ones_like(z)
+        mask[:, :, ::3] = 0
+    kw = dict(sample_cutoff=-1.0, mask_temperature=0.0)
+    want = orc.generate(cb, z.clone(), None if mask is None else mask.clone(), _sampling_steps=steps, rng="philox",
+                        philox_key=(9, 0), logits_fn=_teacher_forced(model, codec), **kw)
+    got = model.generate(codec, start_tokens=z.cuda(), mask=None if mask is None else mask.cuda(), _sampling_steps=steps,
+                         seed=9, return_signal=False, **kw).cpu()
+    assert torch.equal(got, want)
+    if case == "nothing_masked":
+        assert torch.equal(got, z)
+    assert not (got == cfg.mask_token).any()
+
+
+def test_long_context_forward_T3072():
+    """BASELINE.json configs[4] sequence length (T = 3072) on a narrow model: attention tiling, the constant-bias
+    fast path far from the diagonal and the Toeplitz lookups near it, against the bf16-operand oracle."""
+    cfgd = dict(n_heads=4, n_layers=1, n_codebooks=4, n_conditioning_codebooks=0, embedding_dim=256)
+    cfg, sd, model, cb, codec = build(cfgd)
+    z = torch.randint(0, 1025, (1, 4, 3072), generator=torch.Generator().manual_seed(4))
+    got = model.forward_codes(z.cuda(), codec).cpu()  # (B, S, V)
+    orc = vo.OracleVampNet(cfg, sd, "bf16")
+    ref = orc.forward(orc.from_codes(z, cb)).permute(0, 2, 1)
+    e = (got - ref).abs()
+    print(f"T=3072: max {e.max():.3e} mean {e.mean():.3e}")
+    assert e.max() < 2e-2 and e.mean() < 3e-3
