@@ -128,7 +128,8 @@ struct DevBuf {
 struct GraphKey {  // graphs bake pointers, so generate() stages z/mask/out in workspace-owned buffers
   int steps;
   bool has_mask;
-  bool operator<(const GraphKey& o) const { return std::tie(steps, has_mask) < std::tie(o.steps, o.has_mask); }
+  bool top_p;  // selects the sampler kernel variant
+  bool operator<(const GraphKey& o) const { return std::tie(steps, has_mask, top_p) < std::tie(o.steps, o.has_mask, o.top_p); }
 };
 
 struct Workspace {
@@ -350,7 +351,7 @@ int32_t vnb_get_hidden(vnb_model* m, float* out, void* stream) {
 }
 
 static int enqueue_generate(vnb_model* m, Workspace* ws, const int64_t* z, const int32_t* mask, int steps, int64_t* out,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool use_top_p) {
   const vnb_config& c = m->cfg;
   const int ncc = c.n_conditioning_codebooks;
   LAUNCH(FAM_STATE, launch_gen_init(z, mask, ws->zcur.as<int32_t>(), ws->zorig.as<int32_t>(), ws->n0.as<int32_t>(), ws->B, c.n_codebooks,
@@ -367,7 +368,7 @@ static int enqueue_generate(vnb_model* m, Workspace* ws, const int64_t* z, const
     LAUNCH(FAM_EMBED, launch_embed_codes(ws->zcur.as<int32_t>(), m->w.emb_table, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), ws->M,
                           c.n_codebooks, c.vocab_size + 1, c.d_model, st, ws->y.p, ws->ssA.as<float>(), ws->ss_parts));
     if (run_stack(m, ws, ws->logits.as<float>(), st)) return 1;
-    LAUNCH(FAM_SAMPLE, launch_sample_step_dev(sa, ws->dyn.as<SampleDyn>() + i, st));
+    LAUNCH(FAM_SAMPLE, launch_sample_step_dev(sa, ws->dyn.as<SampleDyn>() + i, st, use_top_p));
     ++g_launches;  // sample step = two kernels
   }
   LAUNCH(FAM_STATE, launch_gen_finish(ws->tokens.as<int32_t>(), ws->zorig.as<int32_t>(), out, ws->B, c.n_codebooks, ws->T, ncc, st));
@@ -398,7 +399,8 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   }
   // pageable source: the runtime stages it before returning, so `dyn` may die at scope exit
   CK(cudaMemcpyAsync(ws->dyn.p, dyn.data(), sizeof(SampleDyn) * steps, cudaMemcpyHostToDevice, st));
-  if (!p->use_graph || m->prof.on) return enqueue_generate(m, ws, z, mask, steps, out, st);
+  const bool use_top_p = p->top_p > 0.f && p->top_p < 1.f;
+  if (!p->use_graph || m->prof.on) return enqueue_generate(m, ws, z, mask, steps, out, st, use_top_p);
 
   const size_t nz = static_cast<size_t>(B) * m->cfg.n_codebooks * T;
   CK(cudaMemcpyAsync(ws->z_in.p, z, nz * 8, cudaMemcpyDeviceToDevice, st));
@@ -406,7 +408,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   const int64_t* gz = ws->z_in.as<int64_t>();
   const int32_t* gmask = mask ? ws->mask_in.as<int32_t>() : nullptr;
   int64_t* gout = ws->z_out.as<int64_t>();
-  GraphKey key{steps, mask != nullptr};
+  GraphKey key{steps, mask != nullptr, use_top_p};
   auto it = ws->graphs.find(key);
   if (it == ws->graphs.end()) {
     cudaStream_t cap;
@@ -415,7 +417,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
     cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) { cudaStreamDestroy(cap); return fail("begin capture: %s", cudaGetErrorString(e)); }
     const unsigned long long before = g_launches;
-    int rc = enqueue_generate(m, ws, gz, gmask, steps, gout, cap);
+    int rc = enqueue_generate(m, ws, gz, gmask, steps, gout, cap, use_top_p);
     const unsigned long long in_graph = g_launches - before;
     g_launches = before;
     e = cudaStreamEndCapture(cap, &graph);
@@ -480,7 +482,7 @@ int32_t vnb_sample_step(const float* logits, int32_t* zflat, int32_t* tokens_out
   SampleArgs sa;
   sa.logits = logits; sa.zcur = zflat; sa.zorig = nullptr; sa.tokens = tokens_out; sa.conf = conf_out; sa.n0 = n0;
   sa.B = B; sa.T = S; sa.C = 1; sa.ncc = 0; sa.V = V; sa.mask_token = mask_token;
-  CK(launch_sample_step_dev(sa, dd, st));
+  CK(launch_sample_step_dev(sa, dd, st, false));
   return 0;
 }
 

@@ -92,6 +92,7 @@ struct SampleArgs {
   const int32_t* n0;    // device scalar
   int B, T, C, ncc, V, mask_token;
 };
-cudaError_t launch_sample_step_dev(const SampleArgs& a, const SampleDyn* dyn_dev, cudaStream_t st);
+// use_top_p selects the kernel variant at launch time (it is baked into a captured graph: part of the graph key)
+cudaError_t launch_sample_step_dev(const SampleArgs& a, const SampleDyn* dyn_dev, cudaStream_t st, bool use_top_p);
 
 }  // namespace vnb

@@ -51,7 +51,9 @@ struct SampleStatic {
   int B, T, C, ncc, V, mask_token;
 };
 
-__global__ void __launch_bounds__(256) sample_rows_kernel(const SampleStatic a, const SampleDynDev* __restrict__ dynp) {
+// TOPP = false compiles the nucleus filter out (its 32 extra live registers cost occupancy on the common path)
+template <bool TOPP>
+__global__ void __launch_bounds__(256, TOPP ? 2 : 3) sample_rows_kernel(const SampleStatic a, const SampleDynDev* __restrict__ dynp) {
   const SampleDynDev dyn = *dynp;
   const int Cp = a.C - a.ncc;
   const int S = a.T * Cp;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const SampleStatic a, 
   // removed when the softmax mass of the tokens strictly before it exceeds top_p ("shift right by one" keeps the
   // first token over the threshold).  Equivalent per-token rule: keep v iff sum_{u: x_u > x_v} p_u <= top_p.
   // The smallest kept key is found by bisection over the order-preserving uint image of the floats.
-  if (dyn.top_p > 0.f && dyn.top_p < 1.f) {
+  if (TOPP && dyn.top_p > 0.f && dyn.top_p < 1.f) {
     const float gm = warp_max(mx);
     float pr[MAXV4 * 4];
     float ps = 0.f;
@@ -314,13 +316,14 @@ __global__ void __launch_bounds__(1024) remask_kernel(const SampleStatic a, cons
   }
 }
 
-cudaError_t launch_sample_step_dev(const SampleArgs& s, const SampleDyn* dyn_dev, cudaStream_t st) {
+cudaError_t launch_sample_step_dev(const SampleArgs& s, const SampleDyn* dyn_dev, cudaStream_t st, bool use_top_p) {
   SampleStatic a;
   a.logits = s.logits; a.zcur = s.zcur; a.zorig = s.zorig; a.tokens = s.tokens; a.conf = s.conf; a.n0 = s.n0;
   a.B = s.B; a.T = s.T; a.C = s.C; a.ncc = s.ncc; a.V = s.V; a.mask_token = s.mask_token;
   if (s.V % 128 != 0 || s.V > 1024) return cudaErrorInvalidValue;
   const int rows = s.B * s.T * (s.C - s.ncc);
-  sample_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(a, dyn_dev);
+  if (use_top_p) sample_rows_kernel<true><<<(rows + 7) / 8, 256, 0, st>>>(a, dyn_dev);
+  else sample_rows_kernel<false><<<(rows + 7) / 8, 256, 0, st>>>(a, dyn_dev);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   remask_kernel<<<s.B, 1024, 0, st>>>(a, dyn_dev);
