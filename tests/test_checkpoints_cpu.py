@@ -75,7 +75,10 @@ def test_pack_weights_layout_cpu():
     lut = vo.relative_position_bucket_lut(3072)
     rel = torch.arange(-REL_SAT, REL_SAT + 1)
     assert torch.equal(relative_position_bucket(rel), lut[rel + 3071])
-    assert p["rel_bias"].shape == (2 * REL_SAT + 1, 4)
+    # ... cut at the saturation distance found from the bucket function (91: SURVEY.md §A.3)
+    assert m._rel_sat == 91 and p["rel_bias"].shape == (2 * 91 + 1, 4)
+    E = sd["transformer.layers.0.self_attn.relative_attention_bias.weight"]
+    assert torch.equal(p["rel_bias"][0], E[15]) and torch.equal(p["rel_bias"][-1], E[31]) and torch.equal(p["rel_bias"][91], E[0])
 
 
 def test_codec_load_roundtrip_with_weight_norm(tmp_path):

@@ -151,8 +151,6 @@ struct RvqArgs {
 __global__ void __launch_bounds__(256) rvq_kernel(const RvqArgs a) {
   __shared__ float res[RQ_T][RQ_MAXD];
   __shared__ float e[RQ_T][8], en[RQ_T][8], qv[RQ_T][8];
-  __shared__ float best_v[RQ_T][8];
-  __shared__ int best_i[RQ_T][8];
   __shared__ int sel[RQ_T];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * RQ_T;

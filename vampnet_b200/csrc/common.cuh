@@ -12,10 +12,6 @@
 
 namespace vnb {
 
-#ifndef VNB_SPIN_LIMIT
-#define VNB_SPIN_LIMIT (1u << 26)
-#endif
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

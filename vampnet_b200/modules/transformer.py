@@ -374,9 +374,12 @@ class VampNet(nn.Module):
                                                     _lib.stream_ptr(self.device)))
         return logits
 
-    def hidden_state(self) -> torch.Tensor:
-        """fp32 residual stream after the last layer of the most recent forward (debug tap)."""
-        raise NotImplementedError
+    def hidden_state(self, B: int, T: int) -> torch.Tensor:
+        """fp32 residual stream (B, T, d) after the last layer of the most recent forward of that shape (debug tap)."""
+        out = torch.empty(B, T, self.embedding_dim, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vnb_get_hidden(self._handle, _lib.ptr(out), _lib.stream_ptr(self.device)))
+        return out
 
     # ------------------------------------------------------------------ generate
     @torch.inference_mode()
