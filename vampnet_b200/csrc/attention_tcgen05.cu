@@ -315,12 +315,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  int dev;
+  if (once.need(&dev)) {
     cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ATT_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    once.mark(dev);
   }
   if (p.sat > ATT_MAX_SAT || p.sat < 1) return cudaErrorInvalidValue;
   AttnArgs a;

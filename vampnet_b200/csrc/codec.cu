@@ -114,11 +114,9 @@ cudaError_t launch_conv1d(const float* x, const float* w, const float* bias, con
   ConvArgs a{x, w, bias, alpha, resid, y, B, Cin, Tin, Cout, Tout, K, stride, dil, pad, out_stride, out_off, nq, do_tanh};
   const int span = (CV_TT - 1) * stride + (K - 1) * abs(dil) + 1;
   const size_t smem = (static_cast<size_t>(CV_CI) * span + static_cast<size_t>(CV_CI) * K * CV_CO) * sizeof(float);
-  static size_t cur_max = 48 * 1024;
-  if (smem > cur_max) {
+  if (smem > 48 * 1024) {  // idempotent; per call so that it holds on whichever device is current
     cudaError_t e = cudaFuncSetAttribute(conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    cur_max = smem;
   }
   dim3 grid((nq + CV_TT - 1) / CV_TT, (Cout + CV_CO - 1) / CV_CO, B);
   conv1d_kernel<<<grid, 256, smem, st>>>(a);

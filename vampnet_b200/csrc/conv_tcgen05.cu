@@ -312,14 +312,14 @@ int32_t vnb_codec_conv_tc(const void* a_hi, const void* a_lo, int32_t B, int32_t
   if (!make_tmap_3d(&tAh, a_hi, B, rows, cols, cols, CT_BM, CT_BK) || !make_tmap_3d(&tAl, a_lo, B, rows, cols, cols, CT_BM, CT_BK) ||
       !make_tmap_2d(&tWh, w_hi, N, Ktot, g.BN, CT_BK) || !make_tmap_2d(&tWl, w_lo, N, Ktot, g.BN, CT_BK))
     return vnb_set_error_cuda(tmap_error(), 1);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce once;
+  int dev;
+  if (once.need(&dev)) {
     cudaError_t e = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM);
     if (e != cudaSuccess) return vnb_set_error_cuda("cudaFuncSetAttribute(conv_tcgen05_kernel)", static_cast<int>(e));
-    attr = true;
+    once.mark(dev);
   }
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int sms = device_sm_count();
   const int tiles = B * ((Tq + CT_BM - 1) / CT_BM) * ((N + g.BN - 1) / g.BN);
   conv_tcgen05_kernel<<<tiles < sms ? tiles : sms, CT_THREADS, CT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
       tAh, tAl, tWh, tWl, g);
@@ -341,11 +341,9 @@ int32_t vnb_codec_conv_in(const float* x, const float* w, const float* bias, con
 int32_t vnb_codec_conv_out(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* audio, int32_t B,
                            int32_t T, int32_t C, int32_t K, int32_t pad, void* stream) {
   const size_t smem = (static_cast<size_t>(256 + K - 1) * C + static_cast<size_t>(K) * C) * sizeof(float);
-  static size_t cur = 48 * 1024;
-  if (smem > cur) {
+  if (smem > 48 * 1024) {  // cheap and idempotent; set on every call so that it holds on whichever device is current
     cudaError_t e = cudaFuncSetAttribute(codec_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return vnb_set_error_cuda("cudaFuncSetAttribute(codec_out_kernel)", static_cast<int>(e));
-    cur = smem;
   }
   dim3 grid((T + 255) / 256, B);
   codec_out_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(

@@ -383,18 +383,15 @@ static int g_num_sms = 0;
 
 template <int EPI>
 static cudaError_t launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  int dev;
+  if (once.need(&dev)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GEMM_SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    once.mark(dev);
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  g_num_sms = device_sm_count();
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   gemm_tcgen05_kernel<EPI><<<grid, gemm_threads<EPI>(), GEMM_SMEM, st>>>(tmA, tmB, g);

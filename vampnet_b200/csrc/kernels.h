@@ -8,6 +8,26 @@
 
 namespace vnb {
 
+// Function attributes (max dynamic smem) are per device: remember them per (kernel, device), not per process.
+struct PerDeviceOnce {
+  unsigned long long done = 0;  // bit d = attribute already set on device d
+  bool need(int* dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    return dev >= 64 || !((done >> dev) & 1ull);
+  }
+  void mark(int dev) { if (dev < 64) done |= 1ull << dev; }
+};
+inline int device_sm_count() {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
+  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
+}
+
 // ---- TMA tensor maps (driver entry point fetched at run time; no link-time libcuda dependency) ----
 // 2-D bf16 row-major (rows, cols) with a (box_rows x 64) box, 128B swizzle.
 bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
