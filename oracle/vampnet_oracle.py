@@ -445,3 +445,27 @@ def coarse_to_fine(z, mask, n_c2f, n_cond, chunk_len, mask_token, gen_fn):
         fine.append(gen_fn(chunk, mc))
     fine = torch.cat(fine, dim=-1)
     return fine[:, :, :length].clone(), apply_mask(fine, mask, mask_token)[0][:, :, :length].clone()
+
+
+def vamp(codes, mask, batch_size, feedback_steps, time_stretch_factor, n_coarse, n_c2f, n_cond, coarse_chunk_len,
+         c2f_chunk_len, mask_token, coarse_gen, c2f_gen):
+    """interface.py:491-562.  coarse_gen / c2f_gen(start_tokens, mask) -> tokens stand in for the two generate()
+    calls (the reference forwards **kwargs to the coarse one and pins the fine one to 2 steps, :545-551).
+    Returns (z, mask_z) like return_mask=True."""
+    z = codes.expand(batch_size, -1, -1)
+    mask = mask.expand(batch_size, -1, -1)
+    if time_stretch_factor > 1:  # :510-516
+        z = z.repeat_interleave(time_stretch_factor, dim=-1)
+        mask = mask.repeat_interleave(time_stretch_factor, dim=-1)
+        added = torch.ones_like(mask)
+        added[:, :, ::time_stretch_factor] = 0
+        mask = (mask.bool() | added.bool()).long()
+    zv = z
+    for i in range(feedback_steps):  # :522-532
+        zv, mask_z = coarse_vamp(zv, mask, n_coarse, coarse_chunk_len, mask_token, coarse_gen)
+        mask_z = mask_z.roll(shifts=(i + 1) % feedback_steps, dims=-1)
+    if zv.shape[1] < z.shape[1]:  # :536-541
+        zv = torch.cat([zv, z[:, n_coarse:, :]], dim=1)
+    zv, fine_mask = coarse_to_fine(zv, mask, n_c2f, n_cond, c2f_chunk_len, mask_token, c2f_gen)
+    mask_z = torch.cat([mask_z[:, :n_coarse, :], fine_mask[:, n_coarse:, :]], dim=1)
+    return zv, mask_z

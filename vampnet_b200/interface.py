@@ -163,101 +163,112 @@ class Interface(torch.nn.Module):
         raise RuntimeError("make_beat_mask needs the WaveBeat tracker (interface.py:226-322), a separate model "
                            "outside the hot path (SURVEY.md §2 row 9)")
 
+    # ------------------------------------------------------------------ chunk helpers
+    @staticmethod
+    def _spans(total: int, span: int):
+        """[lo, hi) frame ranges of consecutive chunks of `span` frames covering `total` frames."""
+        return [(lo, min(lo + span, total)) for lo in range(0, total, span)]
+
     # ------------------------------------------------------------------ coarse -> fine (interface.py:327-380)
     @torch.inference_mode()
     def coarse_to_fine(self, z: torch.Tensor, mask: torch.Tensor = None, return_mask: bool = False, **kwargs):
+        """Fill the fine codebooks given the coarse ones, c2f.chunk_size_s seconds at a time.  The sequence is
+        zero-padded to a whole number of chunks (padding frames masked), missing codebooks are appended as zeros and
+        the conditioning codebooks are never masked; every chunk is an independent generate() call."""
         assert self.c2f is not None, "No coarse2fine model loaded"
-        length = z.shape[-1]
-        chunk_len = self.s2t(self.c2f.chunk_size_s)
-        n_chunks = math.ceil(z.shape[-1] / chunk_len)
-        if length % chunk_len != 0:  # zero pad to a whole number of chunks; padding frames are masked
-            pad_len = chunk_len - (length % chunk_len)
-            z = torch.nn.functional.pad(z, (0, pad_len))
-            mask = torch.nn.functional.pad(mask, (0, pad_len), value=1) if mask is not None else None
-        n_append = self.c2f.n_codebooks - z.shape[1]
-        if n_append > 0:
-            z = torch.cat([z, torch.zeros(z.shape[0], n_append, z.shape[-1], dtype=torch.long, device=z.device)], dim=1)
-        if mask is not None:  # conditioning codebooks are never masked
+        n_frames = z.shape[-1]
+        span = self.s2t(self.c2f.chunk_size_s)
+        tail = (-n_frames) % span
+        if tail:
+            z = torch.nn.functional.pad(z, (0, tail))
+            if mask is not None:
+                mask = torch.nn.functional.pad(mask, (0, tail), value=1)
+        missing = self.c2f.n_codebooks - z.shape[1]
+        if missing > 0:
+            z = torch.cat([z, z.new_zeros(z.shape[0], missing, z.shape[-1])], dim=1)
+        if mask is not None:
             mask = mask.clone()
             mask[:, :self.c2f.n_conditioning_codebooks, :] = 0
-        fine_z = []
-        for i in range(n_chunks):
-            chunk = z[:, :, i * chunk_len:(i + 1) * chunk_len]
-            mask_chunk = mask[:, :, i * chunk_len:(i + 1) * chunk_len] if mask is not None else None
-            fine_z.append(self.c2f.generate(codec=self.codec, time_steps=chunk_len, start_tokens=chunk,
-                                            return_signal=False, mask=mask_chunk, cfg_guidance=None, **kwargs))
-        fine_z = torch.cat(fine_z, dim=-1)
-        if return_mask:
-            return fine_z[:, :, :length].clone(), pmask.apply_mask(fine_z, mask, self.c2f.mask_token)[0][:, :, :length].clone()
-        return fine_z[:, :, :length].clone()
+        parts = []
+        for lo, hi in self._spans(z.shape[-1], span):
+            parts.append(self.c2f.generate(codec=self.codec, time_steps=span, start_tokens=z[..., lo:hi],
+                                           mask=None if mask is None else mask[..., lo:hi], return_signal=False,
+                                           cfg_guidance=None, **kwargs))
+        fine = torch.cat(parts, dim=-1)
+        result = fine[..., :n_frames].clone()
+        if not return_mask:
+            return result
+        remasked, _ = pmask.apply_mask(fine, mask, self.c2f.mask_token)
+        return result, remasked[..., :n_frames].clone()
 
     # ------------------------------------------------------------------ coarse (interface.py:382-452)
     @torch.inference_mode()
     def coarse_vamp(self, z, mask, return_mask=False, gen_fn=None, **kwargs):
-        nc = self.coarse.n_codebooks
-        cz = z[:, :nc, :].clone()
-        mask = mask[:, :nc, :]
-        chunk_len = self.s2t(self.coarse.chunk_size_s)
-        n_chunks = math.ceil(cz.shape[-1] / chunk_len)
-        cz_masked_chunks, cz_vamped_chunks = [], []
-        gen_fn = gen_fn or self.coarse.generate
-        for i in range(n_chunks):
-            chunk = cz[:, :, i * chunk_len:(i + 1) * chunk_len]
-            mask_chunk = mask[:, :, i * chunk_len:(i + 1) * chunk_len]
-            # first and last frame of a chunk are kept as anchors when the chunk has any unmasked frame, so that
-            # stitched chunks do not jump (interface.py:407-413)
-            if torch.any(mask_chunk == 0):
-                mask_chunk = mask_chunk.clone()
-                mask_chunk[:, :, 0] = 0
-                mask_chunk[:, :, -1] = 0
-            cz_masked_chunk, mask_chunk = pmask.apply_mask(chunk, mask_chunk, self.coarse.mask_token)
-            cz_masked_chunks.append(cz_masked_chunk[:, :nc, :])
-            cz_vamped_chunks.append(gen_fn(codec=self.codec, time_steps=chunk_len, start_tokens=cz_masked_chunk[:, :nc, :],
-                                           return_signal=False, mask=mask_chunk, **kwargs))
-        cz_masked = torch.cat(cz_masked_chunks, dim=-1)
-        c_vamp = torch.cat(cz_vamped_chunks, dim=-1)
-        c_vamp = torch.cat([c_vamp, z[:, nc:, :]], dim=1)  # fine codes ride along untouched
-        if return_mask:
-            return c_vamp, cz_masked
-        return c_vamp
+        """Regenerate the masked coarse tokens, coarse.chunk_size_s seconds at a time.  A chunk that keeps at least one
+        frame also keeps its first and last frame as anchors so that stitched chunks do not jump
+        (interface.py:407-413).  Fine codebooks ride along untouched."""
+        n_books = self.coarse.n_codebooks
+        tokens, keep = z[:, :n_books, :].clone(), mask[:, :n_books, :]
+        span = self.s2t(self.coarse.chunk_size_s)
+        run = gen_fn or self.coarse.generate
+        starts, results = [], []
+        for lo, hi in self._spans(tokens.shape[-1], span):
+            m = keep[..., lo:hi]
+            if bool((m == 0).any()):
+                m = m.clone()
+                m[..., 0] = 0
+                m[..., -1] = 0
+            start, m = pmask.apply_mask(tokens[..., lo:hi], m, self.coarse.mask_token)
+            starts.append(start)
+            results.append(run(codec=self.codec, time_steps=span, start_tokens=start, mask=m, return_signal=False,
+                               **kwargs))
+        out = torch.cat([torch.cat(results, dim=-1), z[:, n_books:, :]], dim=1)
+        return (out, torch.cat(starts, dim=-1)) if return_mask else out
 
     # ------------------------------------------------------------------ masks (interface.py:454-489)
     def build_mask(self, z: torch.Tensor, sig: AudioSignal = None, rand_mask_intensity: float = 1.0,
                    prefix_s: float = 0.0, suffix_s: float = 0.0, periodic_prompt: int = 7,
                    periodic_prompt_width: int = 1, onset_mask_width: int = 0, _dropout: float = 0.0,
                    upper_codebook_mask: int = 3, ncc: int = 0):
-        mask = pmask.linear_random(z, rand_mask_intensity)
-        mask = pmask.mask_and(mask, pmask.inpaint(z, self.s2t(prefix_s), self.s2t(suffix_s)))
-        mask = pmask.mask_and(mask, pmask.periodic_mask(z, periodic_prompt, periodic_prompt_width, random_roll=True))
+        """1 = regenerate, 0 = keep.  Intersection (mask_and) of: Bernoulli(rand_mask_intensity), kept prefix/suffix,
+        periodic prompt (random roll), optional onset prompt; then time dropout, `ncc` always-kept codebooks and every
+        codebook >= upper_codebook_mask fully masked.  Order and RNG use follow the reference exactly."""
+        layers = [
+            pmask.linear_random(z, rand_mask_intensity),
+            pmask.inpaint(z, self.s2t(prefix_s), self.s2t(suffix_s)),
+            pmask.periodic_mask(z, periodic_prompt, periodic_prompt_width, random_roll=True),
+        ]
         if onset_mask_width > 0:
             assert sig is not None, "must provide a signal to use onset mask"
-            mask = pmask.mask_and(mask, pmask.onset_mask(sig, z, self, width=onset_mask_width))
-        mask = pmask.dropout(mask, _dropout)
-        mask = pmask.codebook_unmask(mask, ncc)
-        mask = pmask.codebook_mask(mask, int(upper_codebook_mask), None)
-        return mask
+            layers.append(pmask.onset_mask(sig, z, self, width=onset_mask_width))
+        mask = layers[0]
+        for other in layers[1:]:
+            mask = pmask.mask_and(mask, other)
+        mask = pmask.codebook_unmask(pmask.dropout(mask, _dropout), ncc)
+        return pmask.codebook_mask(mask, int(upper_codebook_mask), None)
 
     # ------------------------------------------------------------------ vamp (interface.py:491-562)
     def vamp(self, codes: torch.Tensor, mask: torch.Tensor, batch_size: int = 1, feedback_steps: int = 1,
              time_stretch_factor: int = 1, return_mask: bool = False, **kwargs):
+        """codes, mask (1|B, 14, T) -> (B, 14, T'): coarse stage (`feedback_steps` passes, kwargs forwarded to
+        generate) then the fine stage, which the reference pins to 2 sampling steps with default temperature
+        (interface.py:545-551).  time_stretch_factor k > 1 inserts k-1 always-masked frames after every frame."""
         z = codes.expand(batch_size, -1, -1)
         mask = mask.expand(batch_size, -1, -1)
-        if time_stretch_factor > 1:  # new in-between frames are always masked (interface.py:510-516)
-            z = z.repeat_interleave(time_stretch_factor, dim=-1)
-            mask = mask.repeat_interleave(time_stretch_factor, dim=-1)
-            added = torch.ones_like(mask)
-            added[:, :, ::time_stretch_factor] = 0
-            mask = (mask.bool() | added.bool()).long()
+        k = int(time_stretch_factor)
+        if k > 1:
+            z = z.repeat_interleave(k, dim=-1)
+            inserted = torch.ones_like(z)
+            inserted[..., ::k] = 0
+            mask = (mask.repeat_interleave(k, dim=-1).bool() | inserted.bool()).long()
+        n_coarse = self.coarse.n_codebooks
         zv = z
         for i in range(feedback_steps):
-            zv, mask_z = self.coarse_vamp(zv, mask=mask, return_mask=True, **kwargs)
-            mask_z = mask_z.roll(shifts=(i + 1) % feedback_steps, dims=-1)
+            zv, coarse_start = self.coarse_vamp(zv, mask=mask, return_mask=True, **kwargs)
+            coarse_start = coarse_start.roll(shifts=(i + 1) % feedback_steps, dims=-1)
         if zv.shape[1] < z.shape[1]:
-            zv = torch.cat([zv, z[:, self.coarse.n_codebooks:, :]], dim=1)
-        # the c2f stage always runs 2 sampling steps with default temperature (interface.py:545-551)
-        zv, fine_zv_mask = self.coarse_to_fine(zv, mask=mask, typical_filtering=True, _sampling_steps=2,
-                                               return_mask=True)
-        mask_z = torch.cat([mask_z[:, :self.coarse.n_codebooks, :], fine_zv_mask[:, self.coarse.n_codebooks:, :]], dim=1)
-        if return_mask:
-            return zv, mask_z.cpu()
-        return zv
+            zv = torch.cat([zv, z[:, n_coarse:, :]], dim=1)
+        zv, fine_start = self.coarse_to_fine(zv, mask=mask, typical_filtering=True, _sampling_steps=2, return_mask=True)
+        if not return_mask:
+            return zv
+        return zv, torch.cat([coarse_start[:, :n_coarse, :], fine_start[:, n_coarse:, :]], dim=1).cpu()
