@@ -107,6 +107,8 @@ int32_t vnb_sample_step(const float* logits, int32_t* zflat, int32_t* tokens_out
 /* ---- measurement hooks (bench.py) --------------------------------------------------------------
  * vnb_launch_count: kernels launched by this library so far in this process (a graph replay adds the
  * number of kernel nodes it contains).
+ * vnb_graph_capture_count: generate graphs captured so far (a weight hot swap or a repeated call must not
+ * add to it: graphs are cached per (workspace, steps, mask, top_p)).
  * vnb_profile_begin/end: between the two calls every launch of forward/generate is bracketed by CUDA
  * events on the launching stream (graph replay is bypassed so that the events can be recorded);
  * end() returns the summed device time and launch count per kernel family:
@@ -114,6 +116,7 @@ int32_t vnb_sample_step(const float* logits, int32_t* zflat, int32_t* tokens_out
  *   7 gemm_classifier, 8 sample+remask, 9 state init/finish. */
 #define VNB_NUM_FAMILIES 10
 uint64_t vnb_launch_count(void);
+uint64_t vnb_graph_capture_count(void);
 int32_t vnb_profile_begin(vnb_model* m);
 int32_t vnb_profile_end(vnb_model* m, float* ms_per_family, int32_t* launches_per_family, int32_t n_families);
 

@@ -103,3 +103,92 @@ def test_codec_load_roundtrip_with_weight_norm(tmp_path):
     assert x.shape[-1] == 1536 and n == 1000
     with pytest.raises(KeyError):
         DAC(encoder_dim=32, decoder_dim=512).load_flat({"encoder.conv1.weight": torch.zeros(32, 1, 7)})
+
+
+def _save(path, cfg_kwargs, seed, lora):
+    sd = vo.make_state_dict(vo.OracleConfig(**cfg_kwargs), seed=seed, lora=lora)
+    torch.save({"state_dict": sd, "metadata": {"kwargs": dict(cfg_kwargs)}}, path)
+    return sd
+
+
+def test_swap_checkpoint_in_place_resets_adapters_and_rejects_other_architectures(tmp_path):
+    """VampNet.swap_checkpoint (f-4): same architecture -> parameters overwritten in place (module identity and
+    parameter storage kept); going from a LoRA checkpoint to a plain one must leave NO adapter behind (the reference
+    rebuilds the model in reload(), interface.py:146-174, so its lora_B is zero again); different architecture ->
+    False and nothing changes."""
+    from vampnet_b200.modules.transformer import VampNet
+    tuned = _save(tmp_path / "tuned.pth", CFG, seed=0, lora=True)
+    plain = _save(tmp_path / "plain.pth", CFG, seed=5, lora=False)
+    other = dict(CFG, n_layers=3)
+    _save(tmp_path / "other.pth", other, seed=1, lora=False)
+    m = VampNet.load(tmp_path / "tuned.pth")
+    w = m.transformer.layers[0].self_attn.w_qs
+    storage = w.weight.data_ptr()
+    assert w.lora_B.abs().sum() > 0
+    assert m.swap_checkpoint(tmp_path / "plain.pth") is True
+    assert w.weight.data_ptr() == storage  # in place
+    assert torch.equal(w.weight, plain["transformer.layers.0.self_attn.w_qs.weight"])
+    assert w.lora_B.abs().sum() == 0 and torch.equal(w.folded(), w.weight.float())
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    assert m.swap_checkpoint(tmp_path / "other.pth") is False
+    assert all(torch.equal(v, before[k]) for k, v in m.state_dict().items())
+    assert m.swap_checkpoint(tmp_path / "tuned.pth") is True
+    assert torch.equal(w.lora_B, tuned["transformer.layers.0.self_attn.w_qs.lora_B"])
+    # a checkpoint whose metadata omits a key means the constructor default (n_layers 16 != 2 here)
+    sd = vo.make_state_dict(vo.OracleConfig(**CFG), seed=2)
+    torch.save({"state_dict": sd, "metadata": {"kwargs": {k: v for k, v in CFG.items() if k != "n_layers"}}},
+               tmp_path / "implicit.pth")
+    assert m.swap_checkpoint(tmp_path / "implicit.pth") is False
+
+
+def test_interface_model_cache_discovery_and_reload_policy(tmp_path, monkeypatch):
+    """default / available_models / load_finetuned resolve against the local cache layout the reference uses
+    (vampnet/__init__.py:13-76: {coarse,c2f,codec}.pth, loras/<name>/{coarse,c2f}.pth); reload() hot-swaps when the
+    live model accepts the checkpoint and rebuilds otherwise, skipping paths already loaded."""
+    from vampnet_b200 import interface as mod
+    from vampnet_b200.interface import Interface
+    monkeypatch.setenv("VAMPNET_MODELS_DIR", str(tmp_path))
+    assert Interface.available_models() == ["default"]
+    with pytest.raises(RuntimeError, match="local model cache"):
+        Interface.default()
+    for name in ("jazz", "broken", "ambient"):
+        (tmp_path / "loras" / name).mkdir(parents=True)
+        (tmp_path / "loras" / name / "coarse.pth").touch()
+    (tmp_path / "loras" / "jazz" / "c2f.pth").touch()
+    (tmp_path / "loras" / "ambient" / "c2f.pth").touch()
+    assert Interface.available_models() == ["ambient", "jazz", "default"]  # "broken" lacks c2f.pth
+
+    class Live:
+        chunk_size_s = 7
+
+        def __init__(self, accept):
+            self.accept, self.swapped = accept, []
+
+        def swap_checkpoint(self, ckpt):
+            self.swapped.append(Path(ckpt))
+            return self.accept
+
+        def to(self, device):
+            return self
+
+    from pathlib import Path
+    built = []
+
+    def fake_load(ckpt, lora_ckpt=None, device="cpu", chunk_size_s=10):
+        built.append((Path(ckpt), chunk_size_s))
+        return Live(True)
+    monkeypatch.setattr(mod, "_load_model", fake_load)
+    codec = type("Codec", (), {"sample_rate": 44100, "hop_length": 768, "to": lambda self, d: self})()
+    coarse, c2f = Live(accept=True), Live(accept=False)
+    iface = Interface.from_models(codec, coarse, c2f, device="cpu", coarse_chunk_size_s=7, coarse2fine_chunk_size_s=2)
+    with pytest.raises(AssertionError, match="not a valid model name"):
+        iface.load_finetuned("broken")
+    iface.load_finetuned("jazz")
+    jazz = tmp_path / "loras" / "jazz"
+    assert coarse.swapped == [jazz / "coarse.pth"] and iface.coarse is coarse       # hot-swapped, same object
+    assert c2f.swapped == [jazz / "c2f.pth"] and built == [(jazz / "c2f.pth", 2)]   # refused -> rebuilt, chunk kept
+    assert iface.c2f is not c2f and (iface.coarse_path, iface.c2f_path) == (jazz / "coarse.pth", jazz / "c2f.pth")
+    iface.load_finetuned("jazz")  # already loaded: nothing happens
+    assert coarse.swapped == [jazz / "coarse.pth"] and len(built) == 1
+    with pytest.raises(RuntimeError, match="local model cache"):
+        iface.load_finetuned("default")  # coarse.pth / c2f.pth not in the cache root

@@ -204,6 +204,34 @@ def test_workspace_eviction_many_shapes():
                 assert torch.equal(first, out)  # same answer before and after its workspace was evicted
 
 
+def test_hot_swap_keeps_handle_and_graphs():
+    """f-4: load_state_dict on a LIVE model rewrites the packed device buffers in place — the handle, workspaces and
+    captured generate graphs survive (no new capture) and the next generate equals a freshly built model's."""
+    from vampnet_b200 import _lib as L
+    cfg, sd_a, model, cb, codec = build(TINY_COARSE, seed=0, lora=False)
+    _, sd_b, fresh_b, _, _ = build(TINY_COARSE, seed=7, lora=True)
+    z = torch.randint(0, 1024, (2, 4, 40), generator=torch.Generator().manual_seed(2)).cuda()
+    kw = dict(start_tokens=z, _sampling_steps=3, seed=5, return_signal=False, sample_cutoff=-1.0, mask_temperature=0.0)
+    out_a = model.generate(codec, **kw)
+    want_b = fresh_b.generate(codec, **kw)
+    assert not torch.equal(out_a, want_b)
+    handle, ptrs = model._handle.value, {k: v.data_ptr() for k, v in model._packed.items()}
+    captures = L.lib().vnb_graph_capture_count()
+    model.load_state_dict(sd_b, strict=False)
+    assert model._handle.value == handle and ptrs == {k: v.data_ptr() for k, v in model._packed.items()}
+    assert torch.equal(model.generate(codec, **kw), want_b)
+    assert L.lib().vnb_graph_capture_count() == captures  # replayed the graph captured for model A
+    # and back again, dropping the adapter: a plain checkpoint must not inherit lora_B (swap_checkpoint semantics)
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "a.pth")
+        torch.save({"state_dict": sd_a, "metadata": {"kwargs": dict(TINY_COARSE)}}, path)
+        assert model.swap_checkpoint(path) is True
+    assert torch.equal(model.generate(codec, **kw), out_a)
+    assert model._handle.value == handle and L.lib().vnb_graph_capture_count() == captures
+
+
 def test_sampler_distribution_chi_square():
     """RNG parity with torch.multinomial is distributional by construction: with the same logits in
     40 000 positions the empirical token histogram of the CUDA sampler must match softmax(logits / T)."""

@@ -49,6 +49,7 @@ _SIGS = {
     "vnb_generate": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(GenParams),
                                  C.c_void_p, C.c_void_p]),
     "vnb_launch_count": (C.c_uint64, []),
+    "vnb_graph_capture_count": (C.c_uint64, []),
     "vnb_profile_begin": (C.c_int32, [C.c_void_p]),
     "vnb_profile_end": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
     "vnb_sample_step": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

@@ -150,6 +150,7 @@ struct Workspace {
 namespace vnb {
 enum { FAM_EMBED = 0, FAM_RMSNORM, FAM_GEMM_QKV, FAM_ATTN, FAM_GEMM_O, FAM_GEMM_UP, FAM_GEMM_DOWN, FAM_GEMM_CLS,
        FAM_SAMPLE, FAM_STATE, FAM_COUNT };
+static unsigned long long g_captures = 0;  // generate graphs captured + instantiated so far
 static unsigned long long g_launches = 0;  // kernels launched by this library (graph replays add their node count)
 struct Profiler {
   bool on = false;
@@ -434,6 +435,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
       ws->graph_kernels.clear();
     }
     it = ws->graphs.emplace(key, exec).first;
+    ++g_captures;
     ws->graph_kernels[key] = in_graph;
   }
   CK(cudaGraphLaunch(it->second, st));
@@ -443,6 +445,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
 }
 
 uint64_t vnb_launch_count(void) { return g_launches; }
+uint64_t vnb_graph_capture_count(void) { return g_captures; }
 
 int32_t vnb_profile_begin(vnb_model* m) {
   m->prof.used = 0;

@@ -98,26 +98,55 @@ class Interface(torch.nn.Module):
         return self.to(device)
 
     # ------------------------------------------------------------------ checkpoints (interface.py:115-174)
+    # The reference keeps a local cache under <repo>/models/vampnet ({codec,coarse,c2f}.pth, loras/<name>/{coarse,
+    # c2f}.pth) and fills it from the HF hub on a miss (vampnet/__init__.py:19-76).  Here the cache is the only
+    # source: $VAMPNET_MODELS_DIR or ./models/vampnet; a miss raises (no network access in this build).
+    @staticmethod
+    def models_dir() -> Path:
+        import os
+        return Path(os.environ.get("VAMPNET_MODELS_DIR", "./models/vampnet"))
+
     @classmethod
-    def default(cls):
-        raise RuntimeError("Interface.default() downloads checkpoints from the HF hub (vampnet/__init__.py:19-59); "
-                           "this build has no network access. Construct Interface(...) with local checkpoint paths.")
+    def _cached(cls, *parts: str) -> Path:
+        path = cls.models_dir().joinpath(*parts)
+        if not path.exists():
+            raise RuntimeError(f"{path} is not in the local model cache and this build cannot download it from the HF "
+                               f"hub (vampnet/__init__.py:19-59); place the checkpoint there or set VAMPNET_MODELS_DIR")
+        return path
+
+    @classmethod
+    def default(cls, **kwargs):
+        """interface.py:115-126, from the local cache."""
+        wavebeat = cls.models_dir() / "wavebeat.pth"
+        return cls(coarse_ckpt=cls._cached("coarse.pth"), coarse2fine_ckpt=cls._cached("c2f.pth"),
+                   codec_ckpt=cls._cached("codec.pth"), wavebeat_ckpt=str(wavebeat), **kwargs)
 
     @classmethod
     def available_models(cls):
-        return ["default"]
+        """interface.py:128-131: fine-tuned names (those with both coarse.pth and c2f.pth) + "default"."""
+        loras = cls.models_dir() / "loras"
+        names = sorted(d.name for d in loras.iterdir() if (d / "coarse.pth").exists() and (d / "c2f.pth").exists()) \
+            if loras.is_dir() else []
+        return names + ["default"]
 
     def load_finetuned(self, name: str):
-        raise RuntimeError("load_finetuned() downloads from the HF hub; use reload(coarse_ckpt, c2f_ckpt) with local files")
+        """interface.py:134-144."""
+        assert name in self.available_models(), f"{name} is not a valid model name"
+        where = () if name == "default" else ("loras", name)
+        self.reload(coarse_ckpt=self._cached(*where, "coarse.pth"), c2f_ckpt=self._cached(*where, "c2f.pth"))
 
     def reload(self, coarse_ckpt: str = None, c2f_ckpt: str = None):
-        """Swap checkpoints in place (interface.py:146-174)."""
-        if coarse_ckpt is not None and Path(coarse_ckpt) != self.coarse_path:
-            self.coarse = _load_model(ckpt=coarse_ckpt, device=self.device, chunk_size_s=self.coarse.chunk_size_s)
-            self.coarse_path = Path(coarse_ckpt)
-        if c2f_ckpt is not None and Path(c2f_ckpt) != self.c2f_path:
-            self.c2f = _load_model(ckpt=c2f_ckpt, device=self.device, chunk_size_s=self.c2f.chunk_size_s)
-            self.c2f_path = Path(c2f_ckpt)
+        """Swap checkpoints (interface.py:146-174); a checkpoint already loaded is skipped.  A checkpoint of the same
+        architecture is hot-swapped into the live model (VampNet.swap_checkpoint: packed device buffers rewritten in
+        place, workspaces / tensor maps / captured generate graphs kept); otherwise the model is rebuilt."""
+        for attr, path_attr, ckpt in (("coarse", "coarse_path", coarse_ckpt), ("c2f", "c2f_path", c2f_ckpt)):
+            if ckpt is None or getattr(self, path_attr) == Path(ckpt):
+                continue
+            model = getattr(self, attr)
+            if model is None or not model.swap_checkpoint(ckpt):
+                chunk_size_s = model.chunk_size_s if model is not None else (10 if attr == "coarse" else 3)
+                setattr(self, attr, _load_model(ckpt=ckpt, device=self.device, chunk_size_s=chunk_size_s))
+            setattr(self, path_attr, Path(ckpt))
 
     # ------------------------------------------------------------------ unit helpers (interface.py:176-201)
     def s2t(self, seconds: float):

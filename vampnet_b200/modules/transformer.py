@@ -218,6 +218,7 @@ class VampNet(nn.Module):
         self._handle = None       # vnb_model*
         self._packed = None       # dict of device tensors kept alive for the handle
         self._packed_key = None
+        self._packed_codec = None
         self.use_cuda_graph = True
         self.eval()
 
@@ -232,14 +233,61 @@ class VampNet(nn.Module):
         self._handle = None
         self._packed = None
         self._packed_key = None
+        self._packed_codec = None
 
     def _apply(self, fn, *a, **k):
         self._invalidate()
         return super()._apply(fn, *a, **k)
 
-    def load_state_dict(self, *a, **k):
-        self._invalidate()
-        return super().load_state_dict(*a, **k)
+    def load_state_dict(self, state_dict, *a, **k):
+        """Cold model: plain nn.Module load.  Live model (a device handle exists): hot swap — parameters are
+        overwritten in place and the packed device buffers the handle, its tensor maps and its captured generate
+        graphs point at are rewritten in place, so no workspace, tensor map or graph is rebuilt."""
+        live = self._handle is not None and getattr(self, "_packed_codec", None) is not None
+        if not live:
+            self._invalidate()
+            return super().load_state_dict(state_dict, *a, **k)
+        result = super().load_state_dict(state_dict, *a, **k)
+        self.repack()
+        return result
+
+    @torch.no_grad()
+    def repack(self):
+        """Re-fold the current parameters into the live handle's packed buffers (same addresses, same shapes)."""
+        if self._handle is None:
+            return
+        with torch.cuda.device(self.device):
+            fresh = self.pack_weights(self._packed_codec)
+            for name, dst in self._packed.items():
+                src = fresh[name]
+                if src.shape != dst.shape or src.dtype != dst.dtype:
+                    raise RuntimeError(f"packed tensor {name} changed layout {tuple(dst.shape)} -> {tuple(src.shape)}")
+                dst.copy_(src)
+
+    def architecture(self) -> dict:
+        """The constructor arguments that fix the packed layout (what two checkpoints must share to be hot-swappable)."""
+        return dict(n_heads=self.n_heads, n_layers=self.n_layers, n_codebooks=self.n_codebooks,
+                    n_conditioning_codebooks=self.n_conditioning_codebooks, latent_dim=self.latent_dim,
+                    embedding_dim=self.embedding_dim, vocab_size=self.vocab_size)
+
+    @torch.no_grad()
+    def swap_checkpoint(self, location, map_location="cpu") -> bool:
+        """Load another checkpoint of the SAME architecture into this model in place (LoRA checkpoints included).
+        Tensors the checkpoint does not carry go back to their constructor state where that matters for the result
+        (lora_B = 0, i.e. no adapter), which is what the reference gets by building a fresh model in reload()
+        (interface.py:146-174).  Returns False — and changes nothing — when the architecture differs."""
+        blob = torch.load(str(location), map_location=map_location, weights_only=False)
+        import inspect
+        defaults = {k: v.default for k, v in inspect.signature(type(self).__init__).parameters.items()}
+        want = dict(blob.get("metadata", {}).get("kwargs", {}))
+        if any(want.get(k, defaults[k]) != v for k, v in self.architecture().items()):
+            return False
+        sd = blob["state_dict"]
+        for name, prm in self.named_parameters():
+            if name.endswith("lora_B") and name not in sd:
+                prm.zero_()
+        self.load_state_dict(sd, strict=False)
+        return True
 
     def __del__(self):
         try:
@@ -330,6 +378,7 @@ class VampNet(nn.Module):
             torch.cuda.synchronize(self.device)
             _lib.check(lib.vnb_model_create(C.byref(cfg), C.byref(w), C.byref(h)))
         self._handle, self._packed, self._packed_key = h, p, key
+        self._packed_codec = codec
 
     # ------------------------------------------------------------------ forward
     class _NoCodec:
