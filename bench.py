@@ -72,7 +72,10 @@ def gemm_algorithmic_bytes(B, T, d=1280):
 def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch from the committed `ncu --set full` summary
     (profiles/ncu_gemm_r1_final.txt: one layer's qkv / attn-out / ffn-up / ffn-down at the bench shape)."""
-    path = os.path.join(ROOT, "profiles", "ncu_gemm_r1_final.txt")
+    name = "ncu_gemm_r1_pair.txt"  # CTA-pair kernel (current default); older capture of the single-CTA kernel otherwise
+    if not os.path.exists(os.path.join(ROOT, "profiles", name)):
+        name = "ncu_gemm_r1_final.txt"
+    path = os.path.join(ROOT, "profiles", name)
     try:
         per_kind, cur = {}, None
         for line in open(path):
@@ -86,10 +89,10 @@ def ncu_traffic_per_launch():
                 per_kind[cur][-1] += val * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
         # <1> qkv, <2> residual epilogue (attn-out and ffn-down alternate), <3> ffn-up: weight 1 : 2 : 1
         if not all(k in per_kind for k in "123"):
-            return None, "profiles/ncu_gemm_r1_final.txt incomplete"
+            return None, f"profiles/{name} incomplete"
         mean = lambda v: sum(v) / len(v)
         return (mean(per_kind["1"]) + 2 * mean(per_kind["2"]) + mean(per_kind["3"])) / 4.0, \
-            "profiles/ncu_gemm_r1_final.txt (ncu --set full, B=32 T=768 coarse layer)"
+            f"profiles/{name} (ncu --set full, B=32 T=768 coarse layer)"
     except Exception as e:  # the summary is evidence, not a dependency
         return None, f"unavailable: {e}"
 
@@ -384,7 +387,7 @@ def main():
     traffic, traffic_note = ncu_traffic_per_launch()
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {
-        "kernel": "gemm_tcgen05_kernel (all epilogues: qkv, attn-out+residual, ffn-up+GEGLU, ffn-down+residual, classifier+bias)",
+        "kernel": "gemm_tcgen05_kernel<EPI, PAIR=true> (CTA pairs, tcgen05.mma.cta_group::2, 256x256 tiles; all epilogues: qkv, attn-out+residual, ffn-up+GEGLU, ffn-down+residual, classifier+bias)",
         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
         "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write)", "traffic_source": traffic_note,

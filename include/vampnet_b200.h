@@ -117,6 +117,14 @@ int32_t vnb_sample_step(const float* logits, int32_t* zflat, int32_t* tokens_out
 #define VNB_NUM_FAMILIES 10
 uint64_t vnb_launch_count(void);
 uint64_t vnb_graph_capture_count(void);
+
+/* ---- tuning options ----------------------------------------------------------------------------
+ * "gemm_pair": 1 = dense contractions run as CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, each SM stages
+ *              half of the weight tile), 0 = one CTA per 128 x 256 tile.  Results are bit-identical (same
+ *              accumulation order per output element).  Initial value: environment VNB_GEMM_PAIR, else the
+ *              compiled default.  Generate graphs are cached per value. */
+int32_t vnb_set_option(const char* name, int32_t value);
+int32_t vnb_get_option(const char* name, int32_t* value);
 int32_t vnb_profile_begin(vnb_model* m);
 int32_t vnb_profile_end(vnb_model* m, float* ms_per_family, int32_t* launches_per_family, int32_t n_families);
 

@@ -50,6 +50,8 @@ _SIGS = {
                                  C.c_void_p, C.c_void_p]),
     "vnb_launch_count": (C.c_uint64, []),
     "vnb_graph_capture_count": (C.c_uint64, []),
+    "vnb_set_option": (C.c_int32, [C.c_char_p, C.c_int32]),
+    "vnb_get_option": (C.c_int32, [C.c_char_p, C.POINTER(C.c_int32)]),
     "vnb_profile_begin": (C.c_int32, [C.c_void_p]),
     "vnb_profile_end": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
     "vnb_sample_step": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

@@ -100,7 +100,8 @@ bool make_gemm_plan(GemmPlan* p, int epi, const void* A, const void* W, int M, i
   }
   p->M = M; p->N = N; p->K = K; p->epi = epi; p->out = out; p->out2 = out2; p->bias = bias;
   p->T = T; p->Tpad = Tpad; p->d2 = d2;
-  return make_tmap_2d(&p->tmA, A, M, K, 128, 64) && make_tmap_2d(&p->tmB, W, N, K, 256, 64);
+  return make_tmap_2d(&p->tmA, A, M, K, 128, 64) && make_tmap_2d(&p->tmB, W, N, K, 256, 64) &&
+         make_tmap_2d(&p->tmBh, W, N, K, 128, 64);
 }
 
 bool make_attn_plan(AttnPlan* p, const void* qk, const void* vT, void* out, const float* rel, int sat, int B, int T,
@@ -129,7 +130,10 @@ struct GraphKey {  // graphs bake pointers, so generate() stages z/mask/out in w
   int steps;
   bool has_mask;
   bool top_p;  // selects the sampler kernel variant
-  bool operator<(const GraphKey& o) const { return std::tie(steps, has_mask, top_p) < std::tie(o.steps, o.has_mask, o.top_p); }
+  bool pair;   // GEMM tile variant baked into the graph (vnb_set_option "gemm_pair")
+  bool operator<(const GraphKey& o) const {
+    return std::tie(steps, has_mask, top_p, pair) < std::tie(o.steps, o.has_mask, o.top_p, o.pair);
+  }
 };
 
 struct Workspace {
@@ -311,6 +315,7 @@ int32_t vnb_model_create(const vnb_config* cfg, const vnb_weights* w, vnb_model*
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   if (major != 10) return fail("vampnet_b200 needs an sm_100 device (got compute capability major %d)", major);
+  CK(prepare_gemm());
   auto* m = new vnb_model();
   m->cfg = *cfg;
   m->w = *w;
@@ -409,7 +414,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   const int64_t* gz = ws->z_in.as<int64_t>();
   const int32_t* gmask = mask ? ws->mask_in.as<int32_t>() : nullptr;
   int64_t* gout = ws->z_out.as<int64_t>();
-  GraphKey key{steps, mask != nullptr, use_top_p};
+  GraphKey key{steps, mask != nullptr, use_top_p, get_gemm_pair() != 0};
   auto it = ws->graphs.find(key);
   if (it == ws->graphs.end()) {
     cudaStream_t cap;
@@ -446,6 +451,27 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
 
 uint64_t vnb_launch_count(void) { return g_launches; }
 uint64_t vnb_graph_capture_count(void) { return g_captures; }
+
+int32_t vnb_set_option(const char* name, int32_t value) {
+  if (!name) return fail("null option name");
+  if (strcmp(name, "gemm_pair") == 0) {
+    set_gemm_pair(value);
+    return 0;
+  }
+  return fail("unknown option '%s'", name);
+}
+int32_t vnb_get_option(const char* name, int32_t* value) {
+  if (!name || !value) return fail("null argument");
+  if (strcmp(name, "gemm_pair") == 0) {
+    *value = get_gemm_pair();
+    return 0;
+  }
+  if (strcmp(name, "gemm_pair_max_clusters") == 0) {  // read-only: co-resident CTA pairs on the current device
+    *value = get_gemm_max_clusters();
+    return 0;
+  }
+  return fail("unknown option '%s'", name);
+}
 
 int32_t vnb_profile_begin(vnb_model* m) {
   m->prof.used = 0;

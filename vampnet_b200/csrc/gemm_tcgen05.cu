@@ -16,8 +16,14 @@
 //
 // Roofline: tensor-bound.  Algorithmic work = 2*M*N*K flop per launch; bytes (A+W+out) are a few
 // MB against > 10 GFLOP, far right of the ridge.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
+
+#ifndef VNB_GEMM_PAIR_DEFAULT
+#define VNB_GEMM_PAIR_DEFAULT true
+#endif
 
 namespace vnb {
 
@@ -26,8 +32,8 @@ constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_STG_BYTES = 8 * 32 * 36 * 4 - 3072;  // epilogue staging: 4 warps x 32x36 floats, or 8 warps x 32x33 (RESID)
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + GEMM_STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int GEMM_THREADS = 256;
+constexpr int RING_BYTES = STAGES * STAGE_BYTES;  // 192 KiB: 4 x {A 16K, W 32K}, or (CTA pair) 6 x {A 16K, W-half 16K}
+constexpr int GEMM_SMEM = RING_BYTES + GEMM_STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 // The residual epilogue is bound by memory-level parallelism (residual rows must be fetched before they can be
 // updated): it gets 8 epilogue warps, two per TMEM lane quadrant, splitting the 32-column chunks even / odd.
 template <int EPI> constexpr int gemm_epi_warps() { return EPI == VNB_EPI_RESID ? 8 : 4; }
@@ -148,23 +154,36 @@ __device__ __forceinline__ void drain_bf16(__nv_bfloat16* out, int pitch, int M,
   __syncwarp();
 }
 
-template <int EPI>
+// PAIR = true: the CTA-pair variant.  A cluster of two CTAs (one TPC) owns a 256 x 256 output tile; each CTA stages its
+// own 128 rows of A and HALF of the W tile (128 of the 256 rows), the rank-0 CTA issues tcgen05.mma.cta_group::2 with
+// M = 256, and each CTA drains its own 128 accumulator rows.  Per SM this halves the W bytes pulled from L2 into
+// shared memory and read by the tensor core per flop (the kernels run power-capped: bytes moved per flop is what
+// sets the clock), and the smaller stage buys a 6-deep ring in the same 192 KiB.
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmArgs g) {
+  constexpr int NSTAGE = PAIR ? 6 : STAGES;
+  constexpr int W_BYTES = PAIR ? B_BYTES / 2 : B_BYTES;
+  constexpr int STAGE_SZ = A_BYTES + W_BYTES;
+  static_assert(NSTAGE * STAGE_SZ == RING_BYTES, "ring size");
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms are 1024 B: align the tile ring to 1024.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* stg_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + GEMM_STG_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
+  float* stg_all = reinterpret_cast<float*>(smem + RING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES + GEMM_STG_BYTES);
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tfull_bar = empty_bar + NSTAGE;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (g.M + BM - 1) / BM;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;            // 0 = the CTA that issues the MMAs
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int TM = PAIR ? 2 * BM : BM;                          // output rows per tile (per CTA: always BM)
+  const int num_m = (g.M + TM - 1) / TM;
   const int num_n = g.N / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = g.K / BK;
@@ -174,19 +193,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], gemm_epi_warps<EPI>());  // one elected lane of each epilogue warp
+      // one elected lane of each epilogue warp (of both CTAs in a pair: rank 0's barrier gates the next MMA)
+      mbar_init(&tempty_bar[a], gemm_epi_warps<EPI>() * (PAIR ? 2 : 1));
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -195,60 +219,85 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         // n-fastest rasterisation: the N/256 tiles that share an A row-block run concurrently, so A is fetched from
         // HBM once (the weights, <= 13 MB, stay L2-resident).  m-fastest order re-read A 3-4x (ncu dram__bytes).
-        const int m0 = (tile / num_n) * BM;
+        const int m0 = (tile / num_n) * TM + static_cast<int>(rank) * BM;
         const int n0 = (tile % num_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sa = smem + stage * STAGE_SZ;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if constexpr (PAIR) {
+            // both CTAs' bytes are credited to rank 0's barrier, which the MMA thread waits on
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_SZ);
+            const uint32_t bar0 = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(sa, &tmA, bar0, kb * BK, m0);
+            tma_load_2d_pair(sb, &tmB, bar0, kb * BK, n0 + static_cast<int>(rank) * (BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[stage], STAGE_SZ);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+          }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+      if constexpr (PAIR) {
+        // tail: the multicast commits that free the last stages are remote arrivals into THIS CTA's barriers; they
+        // must have landed before the CTA may exit
+        for (int s = 0; s < NSTAGE; ++s) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 150 + stage);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
+        if constexpr (PAIR) mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
+        else mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase, 300 + stage);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_SZ);
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128B swizzle span
-            umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            if constexpr (PAIR)
+              umma_bf16_pair(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        // accumulator complete
+        if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / num_n) * BM;
+      const int m0 = (tile / num_n) * TM + static_cast<int>(rank) * BM;
       const int n0 = (tile % num_n) * BN;
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < g.M;
@@ -369,32 +418,109 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
   }
 
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA may free TMEM / exit while the other still uses the pair
+  else __syncthreads();
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 
+// Single-CTA (128 x 256) or CTA-pair (256 x 256, cta_group::2) kernel: vnb_set_option("gemm_pair", 0|1), else the
+// environment variable VNB_GEMM_PAIR, else the compiled default.
+static int g_gemm_pair = -1;
+void set_gemm_pair(int on) { g_gemm_pair = on ? 1 : 0; }
+static bool gemm_pair_enabled() {
+  if (g_gemm_pair < 0) {
+    const char* e = getenv("VNB_GEMM_PAIR");
+    g_gemm_pair = e != nullptr ? (e[0] == '1') : (VNB_GEMM_PAIR_DEFAULT ? 1 : 0);
+  }
+  return g_gemm_pair == 1;
+}
+int get_gemm_pair() { return gemm_pair_enabled() ? 1 : 0; }
+
+// Once per device and epilogue: opt in to the large dynamic shared memory for both tile variants and ask how many CTA
+// pairs can be co-resident (one CTA per SM, both SMs of a TPC).  Called eagerly by prepare_gemm() (model creation), so
+// that none of this runs inside a stream capture.
+static int g_max_clusters[5][64];
 template <int EPI>
-static cudaError_t launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st) {
+static cudaError_t init_epi() {
   static PerDeviceOnce once;
   int dev;
-  if (once.need(&dev)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GEMM_SMEM);
-    if (e != cudaSuccess) return e;
-    once.mark(dev);
-  }
+  if (!once.need(&dev)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GEMM_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t q = {};
+  q.gridDim = dim3(2 * device_sm_count());
+  q.blockDim = dim3(gemm_threads<EPI>());
+  q.dynamicSmemBytes = GEMM_SMEM;
+  cudaLaunchAttribute qa[1];
+  qa[0].id = cudaLaunchAttributeClusterDimension;
+  qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+  q.attrs = qa; q.numAttrs = 1;
+  int n = 0;
+  e = cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<EPI, true>, &q);
+  if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = device_sm_count() / 2; }
+  if (dev >= 0 && dev < 64) g_max_clusters[EPI][dev] = n;
+  once.mark(dev);
+  return cudaSuccess;
+}
+cudaError_t prepare_gemm() {
+  cudaError_t e;
+  if ((e = init_epi<VNB_EPI_BF16>()) != cudaSuccess) return e;
+  if ((e = init_epi<VNB_EPI_QKV>()) != cudaSuccess) return e;
+  if ((e = init_epi<VNB_EPI_RESID>()) != cudaSuccess) return e;
+  if ((e = init_epi<VNB_EPI_GEGLU>()) != cudaSuccess) return e;
+  return init_epi<VNB_EPI_BIAS_F32>();
+}
+
+int get_gemm_max_clusters() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (prepare_gemm() != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return g_max_clusters[VNB_EPI_RESID][dev];
+}
+
+template <int EPI>
+static cudaError_t launch_epi(const GemmPlan& p, const GemmArgs& g, cudaStream_t st) {
+  cudaError_t e = init_epi<EPI>();
+  if (e != cudaSuccess) return e;
+  int dev = 0;
   g_num_sms = device_sm_count();
+  if (gemm_pair_enabled()) {
+    cudaGetDevice(&dev);
+    const int cap = (dev >= 0 && dev < 64 && g_max_clusters[EPI][dev] > 0) ? g_max_clusters[EPI][dev] : g_num_sms / 2;
+    const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
+    const int clusters = tiles < cap ? tiles : cap;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(gemm_threads<EPI>());
+    cfg.dynamicSmemBytes = GEMM_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI, true>, p.tmA, p.tmBh, g);
+  }
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tcgen05_kernel<EPI><<<grid, gemm_threads<EPI>(), GEMM_SMEM, st>>>(tmA, tmB, g);
+  gemm_tcgen05_kernel<EPI, false><<<grid, gemm_threads<EPI>(), GEMM_SMEM, st>>>(p.tmA, p.tmB, g);
   return cudaGetLastError();
 }
 
@@ -405,11 +531,11 @@ cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t st) {
   g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p.out_bf16); g.ss_out = p.ss_out; g.ss_in = p.ss_in;
   g.ss_parts = p.ss_parts; g.inv_d = p.inv_d; g.eps = p.eps;
   switch (p.epi) {
-    case VNB_EPI_BF16: return launch_epi<VNB_EPI_BF16>(p.tmA, p.tmB, g, st);
-    case VNB_EPI_QKV: return launch_epi<VNB_EPI_QKV>(p.tmA, p.tmB, g, st);
-    case VNB_EPI_RESID: return launch_epi<VNB_EPI_RESID>(p.tmA, p.tmB, g, st);
-    case VNB_EPI_GEGLU: return launch_epi<VNB_EPI_GEGLU>(p.tmA, p.tmB, g, st);
-    case VNB_EPI_BIAS_F32: return launch_epi<VNB_EPI_BIAS_F32>(p.tmA, p.tmB, g, st);
+    case VNB_EPI_BF16: return launch_epi<VNB_EPI_BF16>(p, g, st);
+    case VNB_EPI_QKV: return launch_epi<VNB_EPI_QKV>(p, g, st);
+    case VNB_EPI_RESID: return launch_epi<VNB_EPI_RESID>(p, g, st);
+    case VNB_EPI_GEGLU: return launch_epi<VNB_EPI_GEGLU>(p, g, st);
+    case VNB_EPI_BIAS_F32: return launch_epi<VNB_EPI_BIAS_F32>(p, g, st);
     default: return cudaErrorInvalidValue;
   }
 }

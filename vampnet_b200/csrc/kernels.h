@@ -44,6 +44,7 @@ namespace vnb {
 // ---- GEMM ----
 struct GemmPlan {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmBh;  // W with a 128-row box: the half tile each CTA of a pair stages (gemm_tcgen05.cu, PAIR)
   int M = 0, N = 0, K = 0, epi = 0;
   void* out = nullptr;
   void* out2 = nullptr;
@@ -60,6 +61,10 @@ struct GemmPlan {
 bool make_gemm_plan(GemmPlan* p, int epi, const void* A, const void* W, int M, int N, int K, void* out, void* out2,
                     const float* bias, int T, int Tpad, int d2);
 cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t st);
+cudaError_t prepare_gemm();  // per-device kernel attributes; call outside stream capture
+void set_gemm_pair(int on);  // 1: CTA-pair (cta_group::2) GEMM tiles, 0: single-CTA tiles
+int get_gemm_pair();
+int get_gemm_max_clusters();  // co-resident CTA pairs of the pair kernel on the current device
 cudaError_t launch_gemm_ref(const void* A, const void* W, int M, int N, int K, float* out, cudaStream_t st);
 
 // ---- attention ----

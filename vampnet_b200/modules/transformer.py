@@ -256,7 +256,8 @@ class VampNet(nn.Module):
         """Re-fold the current parameters into the live handle's packed buffers (same addresses, same shapes)."""
         if self._handle is None:
             return
-        with torch.cuda.device(self.device):
+        # the packed tensors may have been created under generate()'s inference_mode: update them in the same mode
+        with torch.inference_mode(), torch.cuda.device(self.device):
             fresh = self.pack_weights(self._packed_codec)
             for name, dst in self._packed.items():
                 src = fresh[name]
