@@ -122,7 +122,12 @@ uint64_t vnb_graph_capture_count(void);
  * "gemm_pair": 1 = dense contractions run as CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, each SM stages
  *              half of the weight tile), 0 = one CTA per 128 x 256 tile.  Results are bit-identical (same
  *              accumulation order per output element).  Initial value: environment VNB_GEMM_PAIR, else the
- *              compiled default.  Generate graphs are cached per value. */
+ *              compiled default.  Generate graphs are cached per value.
+ * "resid_tma": epilogue of the residual GEMMs (x += A.W^T, attention output and FFN down) on CTA pairs: 0 = residual
+ *              rows staged through registers, 1 = residual tiles moved by TMA (in, update in shared memory, out) for
+ *              K <= 1280, 2 = for every residual GEMM.  Bit-identical results.  Initial value: environment
+ *              VNB_RESID_TMA, else the compiled default.
+ * "gemm_pair_max_clusters" (get only): CTA pairs that can be co-resident on the current device. */
 int32_t vnb_set_option(const char* name, int32_t value);
 int32_t vnb_get_option(const char* name, int32_t* value);
 int32_t vnb_profile_begin(vnb_model* m);

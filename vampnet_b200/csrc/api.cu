@@ -70,6 +70,34 @@ bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t col
   }
   return true;
 }
+// Row-major (rows, cols) of fp32 (elem_bytes 4) or bf16 (2) with a (box_rows x box_cols) box whose inner extent is
+// exactly the swizzle span (box_cols * elem_bytes == swizzle_bytes, 64 or 128).
+bool make_tmap_2d_ex(CUtensorMap* tm, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                     uint32_t box_cols, int swizzle_bytes) {
+  auto enc = get_encode();
+  if (!enc) return false;
+  if ((elem_bytes != 2 && elem_bytes != 4) || (swizzle_bytes != 64 && swizzle_bytes != 128) ||
+      static_cast<int>(box_cols) * elem_bytes != swizzle_bytes) {
+    g_tmap_err = "make_tmap_2d_ex: unsupported element size / swizzle / box";
+    return false;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[256];
+    snprintf(b, sizeof(b), "cuTensorMapEncodeTiled(2d ex rows=%llu cols=%llu elem=%d box=%ux%u) -> %d",
+             (unsigned long long)rows, (unsigned long long)cols, elem_bytes, box_rows, box_cols, (int)r);
+    g_tmap_err = b;
+    return false;
+  }
+  return true;
+}
 bool make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
                   uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols) {
   auto enc = get_encode();
@@ -100,8 +128,26 @@ bool make_gemm_plan(GemmPlan* p, int epi, const void* A, const void* W, int M, i
   }
   p->M = M; p->N = N; p->K = K; p->epi = epi; p->out = out; p->out2 = out2; p->bias = bias;
   p->T = T; p->Tpad = Tpad; p->d2 = d2;
-  return make_tmap_2d(&p->tmA, A, M, K, 128, 64) && make_tmap_2d(&p->tmB, W, N, K, 256, 64) &&
-         make_tmap_2d(&p->tmBh, W, N, K, 128, 64);
+  memset(&p->tmR, 0, sizeof(p->tmR));
+  memset(&p->tmO, 0, sizeof(p->tmO));
+  p->has_tmR = p->has_tmO = false;
+  if (!(make_tmap_2d(&p->tmA, A, M, K, 128, 64) && make_tmap_2d(&p->tmB, W, N, K, 256, 64) &&
+        make_tmap_2d(&p->tmBh, W, N, K, 128, 64)))
+    return false;
+  if (epi == VNB_EPI_RESID) {  // residual stream tiles for the TMA epilogue: 32 rows x 32 fp32, 128B-swizzled
+    if (!make_tmap_2d_ex(&p->tmR, out, 4, M, N, 32, 32, 128)) return false;
+    p->has_tmR = true;
+  }
+  return true;
+}
+
+// RESID plans that also produce the next GEMM's operand: bf16 copy of the updated rows + row sums of squares.
+bool gemm_plan_set_fused_out(GemmPlan* p, void* out_bf16, float* ss_out) {
+  p->out_bf16 = out_bf16;
+  p->ss_out = ss_out;
+  if (!make_tmap_2d_ex(&p->tmO, out_bf16, 2, p->M, p->N, 32, 32, 64)) return false;
+  p->has_tmO = true;
+  return true;
 }
 
 bool make_attn_plan(AttnPlan* p, const void* qk, const void* vT, void* out, const float* rel, int sat, int B, int T,
@@ -130,9 +176,9 @@ struct GraphKey {  // graphs bake pointers, so generate() stages z/mask/out in w
   int steps;
   bool has_mask;
   bool top_p;  // selects the sampler kernel variant
-  bool pair;   // GEMM tile variant baked into the graph (vnb_set_option "gemm_pair")
+  int variant;  // GEMM kernel variants baked into the graph (vnb_set_option "gemm_pair", "resid_tma")
   bool operator<(const GraphKey& o) const {
-    return std::tie(steps, has_mask, top_p, pair) < std::tie(o.steps, o.has_mask, o.top_p, o.pair);
+    return std::tie(steps, has_mask, top_p, variant) < std::tie(o.steps, o.has_mask, o.top_p, o.variant);
   }
 };
 
@@ -235,7 +281,7 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   const size_t dd = static_cast<size_t>(d) * d;
   const float inv_d = 1.0f / static_cast<float>(d), eps = 1e-6f;
   auto consumer = [&](GemmPlan& p, const DevBuf& ss) { p.ss_in = ss.as<float>(); p.ss_parts = ws->ss_parts; p.inv_d = inv_d; p.eps = eps; };
-  auto producer = [&](GemmPlan& p, const DevBuf& ss) { p.out_bf16 = ws->y.p; p.ss_out = ss.as<float>(); };
+  auto producer = [&](GemmPlan& p, const DevBuf& ss) { return gemm_plan_set_fused_out(&p, ws->y.p, ss.as<float>()); };
   for (int l = 0; l < L; ++l) {
     // residual stream x (fp32) + its bf16 copy y + row sums of squares: ssA feeds QKV, ssB feeds FFN-up
     bool ok = make_gemm_plan(&ws->qkv[l], VNB_EPI_QKV, ws->y.p, wqkv + l * 3 * dd, ws->M, 3 * d, d, ws->qk.p, ws->vT.p,
@@ -248,9 +294,8 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
                              nullptr, T, ws->Tpad, 0);
     if (!ok) return fail("plan layer %d: %s", l, tmap_error());
     consumer(ws->qkv[l], ws->ssA);
-    producer(ws->wo[l], ws->ssB);
     consumer(ws->up[l], ws->ssB);
-    producer(ws->down[l], ws->ssA);
+    if (!producer(ws->wo[l], ws->ssB) || !producer(ws->down[l], ws->ssA)) return fail("plan layer %d: %s", l, tmap_error());
   }
   if (!make_gemm_plan(&ws->cls, VNB_EPI_BIAS_F32, ws->y.p, m->w.wcls, ws->M, Cp * c.vocab_size, d, ws->logits.p, nullptr,
                       m->w.bcls, T, ws->Tpad, 0))
@@ -414,7 +459,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   const int64_t* gz = ws->z_in.as<int64_t>();
   const int32_t* gmask = mask ? ws->mask_in.as<int32_t>() : nullptr;
   int64_t* gout = ws->z_out.as<int64_t>();
-  GraphKey key{steps, mask != nullptr, use_top_p, get_gemm_pair() != 0};
+  GraphKey key{steps, mask != nullptr, use_top_p, get_gemm_pair() * 4 + get_resid_tma()};
   auto it = ws->graphs.find(key);
   if (it == ws->graphs.end()) {
     cudaStream_t cap;
@@ -458,12 +503,20 @@ int32_t vnb_set_option(const char* name, int32_t value) {
     set_gemm_pair(value);
     return 0;
   }
+  if (strcmp(name, "resid_tma") == 0) {
+    set_resid_tma(value);
+    return 0;
+  }
   return fail("unknown option '%s'", name);
 }
 int32_t vnb_get_option(const char* name, int32_t* value) {
   if (!name || !value) return fail("null argument");
   if (strcmp(name, "gemm_pair") == 0) {
     *value = get_gemm_pair();
+    return 0;
+  }
+  if (strcmp(name, "resid_tma") == 0) {
+    *value = get_resid_tma();
     return 0;
   }
   if (strcmp(name, "gemm_pair_max_clusters") == 0) {  // read-only: co-resident CTA pairs on the current device
