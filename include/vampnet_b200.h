@@ -127,6 +127,9 @@ uint64_t vnb_graph_capture_count(void);
  *              rows staged through registers, 1 = residual tiles moved by TMA (in, update in shared memory, out) for
  *              K <= 1280, 2 = for every residual GEMM.  Bit-identical results.  Initial value: environment
  *              VNB_RESID_TMA, else the compiled default.
+ * "pair_arrive_cta": CTA pairs signal "accumulator drained" to the MMA-issuing CTA with a .cta-scope release instead
+ *              of .release.cluster (which costs a GPU-scope fence per tile and warp).  0 (default, the measured form)
+ *              or 1 (experimental until measured).  Environment VNB_PAIR_ARRIVE_CTA.
  * "gemm_pair_max_clusters" (get only): CTA pairs that can be co-resident on the current device. */
 int32_t vnb_set_option(const char* name, int32_t value);
 int32_t vnb_get_option(const char* name, int32_t* value);

@@ -181,6 +181,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same arrival with the default (.release, .cta-scope) semantics: no MEMBAR.ALL.GPU in front of it.  Enough when the
+// only thing the waiter depends on is work that has already COMPLETED in the arriving thread (tcgen05.ld followed by
+// tcgen05.wait::ld), not memory the waiter is going to read.
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -63,6 +63,7 @@ struct GemmArgs {
   const float* ss_in;       // consumers: partial row sums of squares of THEIR A operand; null = no row scaling
   int ss_parts;             // number of partials to add (fixed order: deterministic)
   float inv_d, eps;         // row scale = rsqrt(sum * inv_d + eps)
+  int flags;                // bit 0: CTA pair, accumulator-drained arrival with .cta-scope release (option "pair_arrive_cta")
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -427,7 +428,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+          if (lane == 0) {
+            const uint32_t bar0 = mapa_u32(smem_u32(&tempty_bar[acc]), 0);
+            if (g.flags & 1) mbar_arrive_remote_cta(bar0);
+            else mbar_arrive_cluster(bar0);
+          }
         }
       }
       if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last stores' reads
@@ -561,7 +566,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        if constexpr (PAIR) {
+          const uint32_t bar0 = mapa_u32(smem_u32(&tempty_bar[acc]), 0);
+          // .release.cluster costs a MEMBAR.ALL.GPU per tile and warp (ncu: 11 % of the residual epilogue's samples);
+          // the .cta-scope form is sufficient here (see common.cuh) and becomes the default once measured
+          if (g.flags & 1) mbar_arrive_remote_cta(bar0);
+          else mbar_arrive_cluster(bar0);
+        }
         else mbar_arrive(&tempty_bar[acc]);
       }
     }
@@ -592,6 +603,17 @@ static bool gemm_pair_enabled() {
   return g_gemm_pair == 1;
 }
 int get_gemm_pair() { return gemm_pair_enabled() ? 1 : 0; }
+
+// "pair_arrive_cta": see GemmArgs::flags bit 0.  Environment VNB_PAIR_ARRIVE_CTA, default 0 (the validated form).
+static int g_pair_arrive_cta = -1;
+void set_pair_arrive_cta(int v) { g_pair_arrive_cta = v ? 1 : 0; }
+int get_pair_arrive_cta() {
+  if (g_pair_arrive_cta < 0) {
+    const char* e = getenv("VNB_PAIR_ARRIVE_CTA");
+    g_pair_arrive_cta = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_pair_arrive_cta;
+}
 
 // Residual GEMMs (attention output, FFN down) with the TMA epilogue: vnb_set_option("resid_tma", v), else the
 // environment variable VNB_RESID_TMA, else the compiled default.  0 = register-staged epilogue, 1 = TMA epilogue when
@@ -699,6 +721,7 @@ cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t st) {
   g.T = p.T; g.Tpad = p.Tpad; g.d2 = p.d2;
   g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p.out_bf16); g.ss_out = p.ss_out; g.ss_in = p.ss_in;
   g.ss_parts = p.ss_parts; g.inv_d = p.inv_d; g.eps = p.eps;
+  g.flags = get_pair_arrive_cta() ? 1 : 0;
   switch (p.epi) {
     case VNB_EPI_BF16: return launch_epi<VNB_EPI_BF16>(p, g, st);
     case VNB_EPI_QKV: return launch_epi<VNB_EPI_QKV>(p, g, st);

@@ -70,6 +70,8 @@ cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t st);
 cudaError_t prepare_gemm();  // per-device kernel attributes; call outside stream capture
 void set_gemm_pair(int on);  // 1: CTA-pair (cta_group::2) GEMM tiles, 0: single-CTA tiles
 int get_gemm_pair();
+void set_pair_arrive_cta(int v);  // CTA pair: accumulator-drained arrival without the cluster-scope fence
+int get_pair_arrive_cta();
 void set_resid_tma(int v);  // residual GEMM epilogue through TMA: 0 off, 1 when K <= 1280, 2 always
 int get_resid_tma();
 int get_gemm_max_clusters();  // co-resident CTA pairs of the pair kernel on the current device
