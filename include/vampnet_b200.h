@@ -130,6 +130,9 @@ uint64_t vnb_graph_capture_count(void);
  * "pair_arrive_cta": CTA pairs signal "accumulator drained" to the MMA-issuing CTA with a .cta-scope release instead
  *              of .release.cluster (which costs a GPU-scope fence per tile and warp).  0 (default, the measured form)
  *              or 1 (experimental until measured).  Environment VNB_PAIR_ARRIVE_CTA.
+ * "attn_p_tmem": attention probabilities go softmax -> tensor memory (tcgen05.st) -> P.V with the A operand read from
+ *              TMEM, instead of through 128B-swizzled shared memory and a generic->async proxy fence.  0 (default, the
+ *              measured form) or 1 (experimental until measured).  Environment VNB_ATTN_P_TMEM.
  * "gemm_pair_max_clusters" (get only): CTA pairs that can be co-resident on the current device. */
 int32_t vnb_set_option(const char* name, int32_t value);
 int32_t vnb_get_option(const char* name, int32_t* value);

@@ -459,7 +459,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   const int64_t* gz = ws->z_in.as<int64_t>();
   const int32_t* gmask = mask ? ws->mask_in.as<int32_t>() : nullptr;
   int64_t* gout = ws->z_out.as<int64_t>();
-  GraphKey key{steps, mask != nullptr, use_top_p, get_gemm_pair() * 8 + get_pair_arrive_cta() * 4 + get_resid_tma()};
+  GraphKey key{steps, mask != nullptr, use_top_p, get_attn_p_tmem() * 16 + get_gemm_pair() * 8 + get_pair_arrive_cta() * 4 + get_resid_tma()};
   auto it = ws->graphs.find(key);
   if (it == ws->graphs.end()) {
     cudaStream_t cap;
@@ -511,6 +511,10 @@ int32_t vnb_set_option(const char* name, int32_t value) {
     set_pair_arrive_cta(value);
     return 0;
   }
+  if (strcmp(name, "attn_p_tmem") == 0) {
+    set_attn_p_tmem(value);
+    return 0;
+  }
   return fail("unknown option '%s'", name);
 }
 int32_t vnb_get_option(const char* name, int32_t* value) {
@@ -525,6 +529,10 @@ int32_t vnb_get_option(const char* name, int32_t* value) {
   }
   if (strcmp(name, "pair_arrive_cta") == 0) {
     *value = get_pair_arrive_cta();
+    return 0;
+  }
+  if (strcmp(name, "attn_p_tmem") == 0) {
+    *value = get_attn_p_tmem();
     return 0;
   }
   if (strcmp(name, "gemm_pair_max_clusters") == 0) {  // read-only: co-resident CTA pairs on the current device

@@ -19,6 +19,8 @@
 //                            (lazy rescale: P may exceed 1 by that factor, harmless in bf16/fp32).
 // Roofline: tensor-bound in FLOPs (4*T^2*64 per (b,h)), but at d_head = 64 the per-block TMEM read
 // (128x64 fp32) and MUFU.EX2 cost as much as the two MMAs; see DESIGN.md.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -76,6 +78,12 @@ __device__ __forceinline__ void pair_barrier(int id) {  // the two warps that sh
   asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
+// PTMEM = true (option "attn_p_tmem", experimental): the probabilities never touch shared memory.  Each softmax thread
+// writes its 32 bf16 P values into tensor memory (tcgen05.st, columns [192,256): two 128 x 64 bf16 tiles) and P.V is
+// issued with the A operand read from TMEM.  This removes the 8 x STS.128 per thread and block, the shared-memory
+// reads of P by the tensor core, and the generic->async proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: 14 % of the
+// kernel's stall samples under ncu, profiles/ncu_attn_r1_final.txt / DESIGN.md §8).
+template <bool PTMEM>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmVT, const AttnArgs a) {
@@ -140,6 +148,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;         // two score buffers: columns [0,64) and [64,128)
   const uint32_t tmem_O = tmem_base + 128;   // columns [128, 192)
+  const uint32_t tmem_P = tmem_base + 192;   // PTMEM: two bf16 P tiles, 32 columns each
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -181,8 +190,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const uint32_t aV = smem_u32(sV + st * V_BYTES);
         const uint32_t aPj = aP + (j & 1) * P_BYTES;
 #pragma unroll
-        for (int k = 0; k < AK / 16; ++k)
-          umma_bf16(tmem_O, umma_desc_sw128(aPj + k * 32), umma_desc_sw128(aV + k * 32), idesc, (j | k) != 0);
+        for (int k = 0; k < AK / 16; ++k) {
+          if constexpr (PTMEM)  // 16 keys = 8 columns of bf16 pairs
+            umma_bf16_ts(tmem_O, tmem_P + (j & 1) * 32 + k * 8, umma_desc_sw128(aV + k * 32), idesc, (j | k) != 0);
+          else
+            umma_bf16(tmem_O, umma_desc_sw128(aPj + k * 32), umma_desc_sw128(aV + k * 32), idesc, (j | k) != 0);
+        }
         umma_commit(&kv_empty[st]);
         umma_commit(&p_free[j & 1]);
         if (j + 2 < nblk) issue_qk(j + 2);
@@ -258,6 +271,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (j >= 2) mbar_wait(&p_free[j & 1], ((j - 2) >> 1) & 1, 555);
       uint64_t psum2 = pack2(0.f, 0.f);
       const uint64_t negm2 = pack2(-m_ref, -m_ref);
+      [[maybe_unused]] uint32_t pall[16];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t pk[4];
@@ -270,12 +284,23 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           psum2 = fadd2(psum2, pack2(p0, p1));
           pk[i] = pack_bf16x2(p0, p1);
         }
-        sts_v4(prow + (((half * 4 + ch) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+        if constexpr (PTMEM) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pall[ch * 4 + i] = pk[i];
+        } else {
+          sts_v4(prow + (((half * 4 + ch) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
       }
       float ps0, ps1;
       unpack2(psum2, ps0, ps1);
       l += ps0 + ps1;
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      if constexpr (PTMEM) {
+        // keys [half*32, half*32+32) of this row -> columns [half*16, half*16+16) of the P tile
+        tmem_st_x16(tmem_P + (j & 1) * 32 + half * 16 + lane_off, pall);
+        tmem_wait_st();
+      } else {
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      }
       tc_fence_before();
       mbar_arrive(&p_full[j & 1]);
     }
@@ -314,12 +339,26 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
+// "attn_p_tmem": 0 = P through shared memory (validated default), 1 = P through tensor memory (experimental until
+// measured).  vnb_set_option, else environment VNB_ATTN_P_TMEM.
+static int g_attn_p_tmem = -1;
+void set_attn_p_tmem(int v) { g_attn_p_tmem = v ? 1 : 0; }
+int get_attn_p_tmem() {
+  if (g_attn_p_tmem < 0) {
+    const char* e = getenv("VNB_ATTN_P_TMEM");
+    g_attn_p_tmem = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_attn_p_tmem;
+}
+
 cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st) {
   static PerDeviceOnce once;
   int dev;
   if (once.need(&dev)) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ATT_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attention_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e != cudaSuccess) return e;
     once.mark(dev);
   }
@@ -329,7 +368,10 @@ cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st) {
   a.rel = p.rel;
   a.sat = p.sat; a.B = p.B; a.T = p.T; a.H = p.H; a.d = p.H * DH;
   dim3 grid((p.T + AQ - 1) / AQ, p.H, p.B);
-  attention_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(p.tmQ, p.tmK, p.tmVT, a);
+  if (get_attn_p_tmem())
+    attention_tcgen05_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(p.tmQ, p.tmK, p.tmVT, a);
+  else
+    attention_tcgen05_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(p.tmQ, p.tmK, p.tmVT, a);
   return cudaGetLastError();
 }
 

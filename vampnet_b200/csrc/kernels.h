@@ -72,6 +72,8 @@ void set_gemm_pair(int on);  // 1: CTA-pair (cta_group::2) GEMM tiles, 0: single
 int get_gemm_pair();
 void set_pair_arrive_cta(int v);  // CTA pair: accumulator-drained arrival without the cluster-scope fence
 int get_pair_arrive_cta();
+void set_attn_p_tmem(int v);  // attention: probabilities through tensor memory instead of shared memory
+int get_attn_p_tmem();
 void set_resid_tma(int v);  // residual GEMM epilogue through TMA: 0 off, 1 when K <= 1280, 2 always
 int get_resid_tma();
 int get_gemm_max_clusters();  // co-resident CTA pairs of the pair kernel on the current device
