@@ -31,7 +31,10 @@ def test_sass_has_blackwell_instructions(built):
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", built], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):  # tcgen05.mma, TMA load, tcgen05.ld
+    # tcgen05.mma, TMA load, tcgen05.ld; the CTA-pair GEMM: cta_group::2 MMA, pair TMA load, multicast commit;
+    # TMA store (residual epilogue variant); tcgen05.st (attention O rescale / P through TMEM)
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "UTMASTG",
+                     "STTM"):
         assert mnemonic in sass, mnemonic
 
 
