@@ -63,7 +63,6 @@ struct GemmArgs {
   const float* ss_in;       // consumers: partial row sums of squares of THEIR A operand; null = no row scaling
   int ss_parts;             // number of partials to add (fixed order: deterministic)
   float inv_d, eps;         // row scale = rsqrt(sum * inv_d + eps)
-  int flags;                // bit 0: CTA pair, accumulator-drained arrival with .cta-scope release (option "pair_arrive_cta")
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -182,7 +181,8 @@ __device__ __forceinline__ void drain_bf16(__nv_bfloat16* out, int pitch, int M,
 // runs a private TMA pipeline over its 32 x 32 fp32 tiles of x: tile in (two loads in flight, no registers held),
 // add the accumulator rows in place in shared memory, tile out, plus the bf16 copy as a second TMA store.  The 128B /
 // 64B swizzles make the lane-per-row accesses bank-conflict free.  Shared memory is paid for with a 3-stage ring.
-template <int EPI, bool PAIR, bool TMAEPI>
+// CTAARRIVE (option "pair_arrive_cta", CTA pairs only): the accumulator-drained arrival uses the .cta-scope release.
+template <int EPI, bool PAIR, bool TMAEPI, bool CTAARRIVE>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
@@ -430,7 +430,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0) {
             const uint32_t bar0 = mapa_u32(smem_u32(&tempty_bar[acc]), 0);
-            if (g.flags & 1) mbar_arrive_remote_cta(bar0);
+            if constexpr (CTAARRIVE) mbar_arrive_remote_cta(bar0);
             else mbar_arrive_cluster(bar0);
           }
         }
@@ -570,7 +570,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t bar0 = mapa_u32(smem_u32(&tempty_bar[acc]), 0);
           // .release.cluster costs a MEMBAR.ALL.GPU per tile and warp (ncu: 11 % of the residual epilogue's samples);
           // the .cta-scope form is sufficient here (see common.cuh) and becomes the default once measured
-          if (g.flags & 1) mbar_arrive_remote_cta(bar0);
+          if constexpr (CTAARRIVE) mbar_arrive_remote_cta(bar0);
           else mbar_arrive_cluster(bar0);
         }
         else mbar_arrive(&tempty_bar[acc]);
@@ -604,7 +604,7 @@ static bool gemm_pair_enabled() {
 }
 int get_gemm_pair() { return gemm_pair_enabled() ? 1 : 0; }
 
-// "pair_arrive_cta": see GemmArgs::flags bit 0.  Environment VNB_PAIR_ARRIVE_CTA, default 0 (the validated form).
+// "pair_arrive_cta": selects the CTAARRIVE instantiations (see the kernel template).  Environment VNB_PAIR_ARRIVE_CTA, default 0 (the validated form).
 static int g_pair_arrive_cta = -1;
 void set_pair_arrive_cta(int v) { g_pair_arrive_cta = v ? 1 : 0; }
 int get_pair_arrive_cta() {
@@ -638,13 +638,19 @@ static cudaError_t init_epi() {
   static PerDeviceOnce once;
   int dev;
   if (!once.need(&dev)) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        GEMM_SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           GEMM_SMEM);
   if (e != cudaSuccess) return e;
   if constexpr (EPI == VNB_EPI_RESID) {
-    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<VNB_EPI_RESID, true, true>,
+    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<VNB_EPI_RESID, true, true, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<VNB_EPI_RESID, true, true, true>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM);
     if (e != cudaSuccess) return e;
   }
@@ -657,7 +663,7 @@ static cudaError_t init_epi() {
   qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
   q.attrs = qa; q.numAttrs = 1;
   int n = 0;
-  e = cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<EPI, true, false>, &q);
+  e = cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<EPI, true, false, false>, &q);
   if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = device_sm_count() / 2; }
   if (dev >= 0 && dev < 64) g_max_clusters[EPI][dev] = n;
   once.mark(dev);
@@ -704,14 +710,20 @@ static cudaError_t launch_epi(const GemmPlan& p, const GemmArgs& g, cudaStream_t
       const bool maps_ok = p.has_tmR && (p.out_bf16 == nullptr || p.has_tmO);
       if (maps_ok && (mode == 2 || (mode == 1 && g.K <= 1280))) {
         cfg.dynamicSmemBytes = TE_SMEM;
-        return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<VNB_EPI_RESID, true, true>, p.tmA, p.tmBh, p.tmR, p.tmO, g);
+        if (get_pair_arrive_cta())
+          return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<VNB_EPI_RESID, true, true, true>, p.tmA, p.tmBh, p.tmR,
+                                    p.tmO, g);
+        return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<VNB_EPI_RESID, true, true, false>, p.tmA, p.tmBh, p.tmR,
+                                  p.tmO, g);
       }
     }
-    return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI, true, false>, p.tmA, p.tmBh, p.tmR, p.tmO, g);
+    if (get_pair_arrive_cta())
+      return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI, true, false, true>, p.tmA, p.tmBh, p.tmR, p.tmO, g);
+    return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI, true, false, false>, p.tmA, p.tmBh, p.tmR, p.tmO, g);
   }
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tcgen05_kernel<EPI, false, false><<<grid, gemm_threads<EPI>(), GEMM_SMEM, st>>>(p.tmA, p.tmB, p.tmR, p.tmO, g);
+  gemm_tcgen05_kernel<EPI, false, false, false><<<grid, gemm_threads<EPI>(), GEMM_SMEM, st>>>(p.tmA, p.tmB, p.tmR, p.tmO, g);
   return cudaGetLastError();
 }
 
@@ -721,7 +733,6 @@ cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t st) {
   g.T = p.T; g.Tpad = p.Tpad; g.d2 = p.d2;
   g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p.out_bf16); g.ss_out = p.ss_out; g.ss_in = p.ss_in;
   g.ss_parts = p.ss_parts; g.inv_d = p.inv_d; g.eps = p.eps;
-  g.flags = get_pair_arrive_cta() ? 1 : 0;
   switch (p.epi) {
     case VNB_EPI_BF16: return launch_epi<VNB_EPI_BF16>(p, g, st);
     case VNB_EPI_QKV: return launch_epi<VNB_EPI_QKV>(p, g, st);
