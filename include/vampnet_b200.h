@@ -133,6 +133,9 @@ uint64_t vnb_graph_capture_count(void);
  * "attn_p_tmem": attention probabilities go softmax -> tensor memory (tcgen05.st) -> P.V with the A operand read from
  *              TMEM, instead of through 128B-swizzled shared memory and a generic->async proxy fence.  0 (default, the
  *              measured form) or 1 (experimental until measured).  Environment VNB_ATTN_P_TMEM.
+ * "attn_v2":     the second attention design (attention2_tcgen05.cu): two 128-query tiles per CTA in ping-pong, 128-key
+ *              blocks, one thread per row, P through tensor memory, one-pass optimistic softmax.  0 (default, the
+ *              measured first design) or 1 (experimental until measured).  Environment VNB_ATTN_V2.
  * "gemm_pair_max_clusters" (get only): CTA pairs that can be co-resident on the current device. */
 int32_t vnb_set_option(const char* name, int32_t value);
 int32_t vnb_get_option(const char* name, int32_t* value);

@@ -5,6 +5,8 @@ bit for bit (same operands, same accumulation order), and a timing line is print
 
   "attn_p_tmem"     attention probabilities through tensor memory (tcgen05.st + A-from-TMEM tcgen05.mma)
   "pair_arrive_cta" CTA-pair GEMM: accumulator-drained arrival without the GPU-scope fence
+  "attn_v2"         second attention design (two query tiles in ping-pong, 128-key blocks, one thread per row, P in
+                    TMEM, one-pass softmax); different blocking, so it is compared within tolerance, not bit for bit
 """
 import os
 
@@ -75,6 +77,57 @@ def test_attention_p_through_tmem(L, B, T, H):
     ref = attention_ref(q, k, v, rel, sat, H)
     assert (got.float() - ref).abs().max() < 3e-2
     assert torch.equal(got, base)  # same P values, same MMA accumulation order
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 64, 1), (1, 128, 1), (1, 129, 2), (2, 100, 4), (1, 3, 2), (1, 256, 2), (1, 257, 1),
+                                   (2, 768, 4), (1, 1000, 2), (1, 3072, 1)])
+def test_attention_v2(L, B, T, H):
+    """Ragged T (partial last key block, a CTA with a single query tile, T < one block), the lookup / constant bias
+    regimes (T > 2*sat) and many blocks (O rescale path: the first block's max is rarely the row max)."""
+    q, k, v, rel, sat, qk, vT, Tpad = attention_inputs(B, T, H, seed=T + 1)
+    prev = set_opt(L, b"attn_v2", 0)
+    try:
+        base = run_attention(L, qk, vT, rel, sat, B, T, Tpad, H)
+        L.check(L.lib().vnb_set_option(b"attn_v2", 1))
+        got = run_attention(L, qk, vT, rel, sat, B, T, Tpad, H)
+    finally:
+        set_opt(L, b"attn_v2", prev)
+    ref = attention_ref(q, k, v, rel, sat, H)
+    e_ref, e_base = (got.float() - ref).abs().max().item(), (got.float() - base.float()).abs().max().item()
+    print(f"attn_v2 B={B} T={T} H={H}: vs torch {e_ref:.3e}, vs first design {e_base:.3e}")
+    assert not torch.isnan(got.float()).any()
+    assert e_ref < 3e-2 and e_base < 3e-2
+
+
+def test_attention_v2_large_logits(L):
+    """Scores with a wide dynamic range force the lazy-rescale path (row max grows by more than 2^8 after block 0)."""
+    B, T, H = 1, 640, 2
+    q, k, v, rel, sat, qk, vT, Tpad = attention_inputs(B, T, H, seed=5)
+    qk = qk.clone()
+    qk[:, 400:, H * 64:] *= 6.0   # keys of the later blocks produce much larger scores
+    prev = set_opt(L, b"attn_v2", 1)
+    try:
+        got = run_attention(L, qk, vT, rel, sat, B, T, Tpad, H)
+    finally:
+        set_opt(L, b"attn_v2", prev)
+    d = H * 64
+    ref = attention_ref(qk[..., :d], qk[..., d:], v, rel, sat, H)
+    assert (got.float() - ref).abs().max() < 5e-2
+
+
+def test_attention_v2_timing(L):
+    B, T, H = 32, 768, 20
+    q, k, v, rel, sat, qk, vT, Tpad = attention_inputs(B, T, H, seed=1)
+    out = torch.empty(B, T, H * 64, device="cuda", dtype=torch.bfloat16)
+    prev = set_opt(L, b"attn_v2", 0)
+    try:
+        for mode in (0, 1):
+            L.check(L.lib().vnb_set_option(b"attn_v2", mode))
+            ms = time_op(lambda: L.lib().vnb_op_attention(L.ptr(qk), L.ptr(vT), L.ptr(out), L.ptr(rel), sat, B, T, Tpad,
+                                                          H, L.stream_ptr()))
+            print(f"attention attn_v2={mode}: {ms * 1e3:.1f} us  {4.0 * B * H * T * T * 64 / ms / 1e9:.0f} TFLOP/s")
+    finally:
+        set_opt(L, b"attn_v2", prev)
 
 
 def time_op(fn, n=20):

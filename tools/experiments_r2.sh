@@ -21,7 +21,7 @@ PY
 }
 echo "##### bench per variant (default first; each ~40 s)"
 i=0
-for cfg in "VNB_NOOP=1" "VNB_PAIR_ARRIVE_CTA=1" "VNB_ATTN_P_TMEM=1" "VNB_PAIR_ARRIVE_CTA=1 VNB_ATTN_P_TMEM=1"; do
+for cfg in "VNB_NOOP=1" "VNB_PAIR_ARRIVE_CTA=1" "VNB_ATTN_P_TMEM=1" "VNB_ATTN_V2=1" "VNB_PAIR_ARRIVE_CTA=1 VNB_ATTN_V2=1"; do
   tag=$(echo "$cfg" | tr ' =' '__')
   env $cfg timeout 240 python bench.py --no-cpu-baseline > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err \
     && summ gpurun_out/bench_$tag.json || tail -n 5 gpurun_out/bench_$tag.err
@@ -34,6 +34,9 @@ for v in 0 1; do
     -o gpurun_out/prof_attn_ptmem$v python tools/profile_step.py > gpurun_out/ncu_attn_ptmem$v.log 2>&1
   echo "ncu attention attn_p_tmem=$v exit=$?"
 done
+VNB_ATTN_V2=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention2 -s 45 -c 1 -f \
+  -o gpurun_out/prof_attn_v2 python tools/profile_step.py > gpurun_out/ncu_attn_v2.log 2>&1
+echo "ncu attention v2 exit=$?"
 VNB_RESID_TMA=2 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 170 -c 4 -f \
   -o gpurun_out/prof_gemm_resid_tma python tools/profile_step.py > gpurun_out/ncu_gemm_resid_tma.log 2>&1
 echo "ncu resid_tma exit=$?"

@@ -155,7 +155,7 @@ bool make_attn_plan(AttnPlan* p, const void* qk, const void* vT, void* out, cons
   const int d = H * 64;
   p->out = out; p->rel = rel; p->sat = sat; p->B = B; p->T = T; p->Tpad = Tpad; p->H = H;
   return make_tmap_3d(&p->tmQ, qk, B, T, 2 * d, 2 * d, 128, 64) && make_tmap_3d(&p->tmK, qk, B, T, 2 * d, 2 * d, 64, 64) &&
-         make_tmap_3d(&p->tmVT, vT, B, d, Tpad, Tpad, 64, 64);
+         make_tmap_3d(&p->tmVT, vT, B, d, Tpad, Tpad, 64, 64) && make_tmap_3d(&p->tmK128, qk, B, T, 2 * d, 2 * d, 128, 64);
 }
 
 // ---------------------------------------------------------------------------------- model
@@ -459,7 +459,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   const int64_t* gz = ws->z_in.as<int64_t>();
   const int32_t* gmask = mask ? ws->mask_in.as<int32_t>() : nullptr;
   int64_t* gout = ws->z_out.as<int64_t>();
-  GraphKey key{steps, mask != nullptr, use_top_p, get_attn_p_tmem() * 16 + get_gemm_pair() * 8 + get_pair_arrive_cta() * 4 + get_resid_tma()};
+  GraphKey key{steps, mask != nullptr, use_top_p, get_attn_v2() * 32 + get_attn_p_tmem() * 16 + get_gemm_pair() * 8 + get_pair_arrive_cta() * 4 + get_resid_tma()};
   auto it = ws->graphs.find(key);
   if (it == ws->graphs.end()) {
     cudaStream_t cap;
@@ -515,6 +515,10 @@ int32_t vnb_set_option(const char* name, int32_t value) {
     set_attn_p_tmem(value);
     return 0;
   }
+  if (strcmp(name, "attn_v2") == 0) {
+    set_attn_v2(value);
+    return 0;
+  }
   return fail("unknown option '%s'", name);
 }
 int32_t vnb_get_option(const char* name, int32_t* value) {
@@ -533,6 +537,10 @@ int32_t vnb_get_option(const char* name, int32_t* value) {
   }
   if (strcmp(name, "attn_p_tmem") == 0) {
     *value = get_attn_p_tmem();
+    return 0;
+  }
+  if (strcmp(name, "attn_v2") == 0) {
+    *value = get_attn_v2();
     return 0;
   }
   if (strcmp(name, "gemm_pair_max_clusters") == 0) {  // read-only: co-resident CTA pairs on the current device

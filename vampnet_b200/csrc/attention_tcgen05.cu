@@ -352,6 +352,7 @@ int get_attn_p_tmem() {
 }
 
 cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st) {
+  if (get_attn_v2()) return launch_attention2(p, st);
   static PerDeviceOnce once;
   int dev;
   if (once.need(&dev)) {

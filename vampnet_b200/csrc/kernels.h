@@ -84,6 +84,7 @@ struct AttnPlan {
   CUtensorMap tmQ;   // (B, T, 2d)  box (1, 128 rows, 64 cols)
   CUtensorMap tmK;   // (B, T, 2d)  box (1, 64 rows, 64 cols)
   CUtensorMap tmVT;  // (B, d, Tpad) box (1, 64 rows, 64 cols)
+  CUtensorMap tmK128;  // (B, T, 2d)  box (1, 128 rows, 64 cols): 128-key blocks of the second attention design
   void* out = nullptr;         // (B, T, d) bf16
   const float* rel = nullptr;  // (2*sat+1, H)
   int sat = 0, B = 0, T = 0, Tpad = 0, H = 0;
@@ -91,6 +92,9 @@ struct AttnPlan {
 bool make_attn_plan(AttnPlan* p, const void* qk, const void* vT, void* out, const float* rel, int sat, int B, int T,
                     int Tpad, int H);
 cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st);
+cudaError_t launch_attention2(const AttnPlan& p, cudaStream_t st);  // attention2_tcgen05.cu (option "attn_v2")
+void set_attn_v2(int v);
+int get_attn_v2();
 
 // ---- elementwise / gather ----
 cudaError_t launch_rmsnorm(const float* x, const float* w, void* y_bf16, int M, int d, float eps, cudaStream_t st);
