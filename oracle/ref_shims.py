@@ -112,11 +112,26 @@ def install():
     mods.__path__ = [os.path.join(REFERENCE_ROOT, "vampnet", "modules")]
     sys.modules["vampnet.modules"] = mods
 
+    # vampnet/interface.py:12,16 imports the beat tracker (librosa) and the codec package (lac); neither is in this
+    # image and neither is touched by the chunking / masking logic that the Interface tests pin, so both are
+    # name-only stubs.
+    beats = types.ModuleType("vampnet.beats")
+    beats.WaveBeat = type("WaveBeat", (), {})
+    sys.modules["vampnet.beats"] = beats
+    for name in ("lac", "lac.model", "lac.model.lac"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m._is_ref_shim = True
+            sys.modules[name] = m
+    sys.modules["lac.model.lac"].LAC = type("LAC", (), {})
+    sys.modules["lac"].model = sys.modules["lac.model"]
+    sys.modules["lac.model"].lac = sys.modules["lac.model.lac"]
+
 
 def uninstall():
     for k in list(sys.modules):
         if k == "vampnet" or k.startswith("vampnet.") or k in (
-            "audiotools", "audiotools.ml", "audiotools.util", "loralib"
+            "audiotools", "audiotools.ml", "audiotools.util", "loralib", "lac", "lac.model", "lac.model.lac"
         ):
             m = sys.modules[k]
             if k.startswith("vampnet") and not getattr(sys.modules.get("vampnet"), "_is_ref_shim", False):
@@ -131,6 +146,12 @@ def load_reference():
     mk = importlib.import_module("vampnet.mask")
     ut = importlib.import_module("vampnet.util")
     return tr, mk, ut
+
+
+def load_reference_interface():
+    """The reference's vampnet/interface.py module (Interface with its own chunking / masking code)."""
+    install()
+    return importlib.import_module("vampnet.interface")
 
 
 class StubCodec:
