@@ -47,3 +47,32 @@ def test_no_product_import_of_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b|from\s+\.+\s*import\s+oracle|importlib.*oracle",
                                      src, re.M), f"{f} imports the oracle"
                 assert "oracle" not in src, f"{f} mentions the oracle"
+
+
+def test_options_are_host_state_with_measured_defaults(built):
+    """vnb_get_option / vnb_set_option are plain host state (no device call): every documented switch exists, the
+    defaults are the MEASURED configuration (CTA-pair GEMM on, every unmeasured variant off), unknown names fail."""
+    import ctypes as C
+    import subprocess
+    import sys
+    code = """
+import ctypes as C, sys
+lib = C.CDLL(sys.argv[1])
+lib.vnb_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
+lib.vnb_set_option.argtypes = [C.c_char_p, C.c_int32]
+lib.vnb_last_error.restype = C.c_char_p
+out = {}
+for name in (b"gemm_pair", b"resid_tma", b"pair_arrive_cta", b"attn_p_tmem", b"attn_v2"):
+    v = C.c_int32(-7)
+    assert lib.vnb_get_option(name, C.byref(v)) == 0, name
+    out[name.decode()] = v.value
+assert out == {"gemm_pair": 1, "resid_tma": 0, "pair_arrive_cta": 0, "attn_p_tmem": 0, "attn_v2": 0}, out
+assert lib.vnb_set_option(b"resid_tma", 2) == 0
+v = C.c_int32()
+lib.vnb_get_option(b"resid_tma", C.byref(v)); assert v.value == 2
+assert lib.vnb_set_option(b"nope", 1) != 0 and b"unknown option" in lib.vnb_last_error()
+print("ok")
+"""
+    env = {k: v for k, v in os.environ.items() if not k.startswith("VNB_")}  # defaults, not the caller's overrides
+    r = subprocess.run([sys.executable, "-c", code, built], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
