@@ -16,6 +16,7 @@ All compute goes through the C ABI (vnb_codec_conv1d, vnb_codec_rvq); there is n
 from __future__ import annotations
 
 import math
+import re
 from pathlib import Path
 from typing import Dict
 
@@ -82,6 +83,75 @@ def _layout(cfg) -> Dict[str, tuple]:
     sh["decoder.snake1.alpha"] = (c,)
     conv("decoder.conv2", 1, c, 7)
     return sh
+
+
+_WN_SUFFIXES = ((".parametrizations.weight.original0", ".weight_g"), (".parametrizations.weight.original1", ".weight_v"))
+
+
+def remap_descript_keys(sd: Dict[str, torch.Tensor], n_blocks: int) -> Dict[str, torch.Tensor]:
+    """descript-audio-codec / ``lac`` state_dict names -> the flat names of :func:`_layout`.
+
+    The reference loads ``lac.model.lac.LAC`` (interface.py:16, 70), a fork of the Descript Audio Codec whose
+    modules are ``nn.Sequential`` stacks, so its checkpoints address tensors by position:
+    ``encoder.block.0`` is the input conv, ``encoder.block.{i+1}.block.{r}.block.{0..3}`` are (snake, conv7, snake,
+    conv1) of residual unit r of block i, ``encoder.block.{i+1}.block.{3,4}`` the block's snake + strided conv,
+    ``encoder.block.{n+1}/{n+2}`` the final snake + conv; the decoder is ``decoder.model.0``, then per block
+    ``.block.0`` snake, ``.block.1`` transposed conv, ``.block.{2,3,4}`` residual units, then ``decoder.model.{n+1}``
+    snake and ``.{n+2}`` output conv.  Weight-norm pairs arrive as ``weight_g``/``weight_v`` (or the newer
+    ``parametrizations.weight.original0/1``) and Snake ``alpha`` as (1, C, 1); both are normalised by
+    :meth:`DAC.load_flat`.  Keys already in the flat layout pass through unchanged.
+    """
+    n = n_blocks
+    unit = {"0.alpha": "snake1.alpha", "1.": "conv1.", "2.alpha": "snake2.alpha", "3.": "conv2."}
+
+    def res_unit(rest: str):
+        for k, v in unit.items():
+            if rest.startswith(k):
+                return v + rest[len(k):] if k.endswith(".") else v
+        raise KeyError(rest)
+
+    out = {}
+    for key, t in sd.items():
+        for a, b in _WN_SUFFIXES:
+            if key.endswith(a):
+                key = key[: -len(a)] + b
+        m = re.match(r"^(encoder\.block|decoder\.model)\.(\d+)\.(.*)$", key)
+        if m is None or re.match(r"^encoder\.block\.\d+\.(res_unit\d|snake1|conv1)\.", key):
+            out[key] = t
+            continue
+        side, idx, rest = m.group(1), int(m.group(2)), m.group(3)
+        enc = side.startswith("encoder")
+        root = "encoder" if enc else "decoder"
+        if idx == 0:
+            new = f"{root}.conv1.{rest}"
+        elif idx == n + 1:
+            new = f"{root}.snake1.{rest}"
+        elif idx == n + 2:
+            new = f"{root}.conv2.{rest}"
+        elif 1 <= idx <= n:
+            mm = re.match(r"^block\.(\d+)\.(.*)$", rest)
+            if mm is None:
+                raise KeyError(f"unrecognised codec key {key}")
+            j, tail = int(mm.group(1)), mm.group(2)
+            blk = f"{root}.block.{idx - 1}"
+            if enc:
+                if j < 3:
+                    new = f"{blk}.res_unit{j + 1}." + res_unit(tail[len("block."):])
+                elif j == 3:
+                    new = f"{blk}.snake1.{tail}"
+                else:
+                    new = f"{blk}.conv1.{tail}"
+            else:
+                if j == 0:
+                    new = f"{blk}.snake1.{tail}"
+                elif j == 1:
+                    new = f"{blk}.conv_t1.{tail}"
+                else:
+                    new = f"{blk}.res_unit{j - 1}." + res_unit(tail[len("block."):])
+        else:
+            raise KeyError(f"unrecognised codec key {key} (expected at most {n + 3} stages)")
+        out[new] = t
+    return out
 
 
 class _Quantizer:
@@ -180,13 +250,19 @@ class DAC(nn.Module):
         self.eval()
 
     # ---- state ---------------------------------------------------------------------------------
-    def _apply(self, fn, *a, **k):
+    def _invalidate(self):
+        """Drop every tensor derived from the parameters (normalised codebooks, split-bf16 / transposed-conv packs);
+        called by parallel.broadcast_module_weights after parameters were overwritten in place."""
         self._pack = None
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
         return super()._apply(fn, *a, **k)
 
     def load_flat(self, weights: Dict[str, torch.Tensor]):
-        """Load a flat {dotted name: tensor} dict (HF DacModel naming).  weight_g / weight_v pairs are folded."""
-        weights = dict(weights)
+        """Load a flat {dotted name: tensor} dict, in the HF DacModel naming or in the descript-audio-codec / lac
+        naming the reference's checkpoints use (see remap_descript_keys).  weight_g / weight_v pairs are folded."""
+        weights = remap_descript_keys(dict(weights), len(self.encoder_rates))
         for k in [k for k in weights if k.endswith(".weight_v")]:
             base = k[: -len("_v")]
             v, gk = weights.pop(k), base + "_g"
@@ -204,11 +280,15 @@ class DAC(nn.Module):
         return self
 
     @classmethod
-    def load(cls, location, *_, **__):
-        """audiotools BaseModel.load layout: {'state_dict': ..., 'metadata': {'kwargs': {...}}} (interface.py:70)."""
+    def load(cls, location, *_, **overrides):
+        """audiotools BaseModel.load layout: {'state_dict': ..., 'metadata': {'kwargs': {...}}} (interface.py:70).
+        Keyword arguments override the checkpoint's constructor arguments (e.g. precision="fp32")."""
         blob = torch.load(str(Path(location)), map_location="cpu", weights_only=False)
         kwargs = dict(blob.get("metadata", {}).get("kwargs", {}))
-        model = cls(**kwargs)
+        kwargs.update(overrides)
+        import inspect
+        known = set(inspect.signature(cls.__init__).parameters) - {"self", "_ignored"}
+        model = cls(**{k: v for k, v in kwargs.items() if k in known})  # e.g. quantizer_dropout is training-only
         sd = {k[len("params."):] if k.startswith("params.") else k: v for k, v in blob["state_dict"].items()}
         model.load_flat(sd)
         return model
