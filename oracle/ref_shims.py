@@ -16,8 +16,11 @@ Shims:
   * ``loralib``     -> Linear(in, out, r=...) implemented as W x + scaling * B A x
     (loralib semantics, lora_alpha=1 default => scaling = 1/r) so that LoRA
     folding in the product can be checked against an unfused evaluation.
-  * ``vampnet``     -> a synthetic package object whose __path__ points at the
-    reference, so vampnet/__init__.py (HF hub + lac + librosa imports) is skipped.
+  * the reference package itself is imported under the name ``vampnet_reference``: a synthetic
+    package object whose __path__ points at /root/reference/vampnet, so vampnet/__init__.py (HF hub +
+    lac + librosa imports) is skipped and the name ``vampnet`` stays free for this repository's own
+    drop-in package (vampnet/ at the repo root).  The reference only uses relative imports inside
+    its package, so the name it is imported under does not matter.
 """
 from __future__ import annotations
 
@@ -33,6 +36,7 @@ import torch
 import torch.nn as nn
 
 REFERENCE_ROOT = os.environ.get("VAMPNET_REFERENCE_ROOT", "/root/reference")
+PKG = "vampnet_reference"
 
 
 def available() -> bool:
@@ -86,7 +90,7 @@ def _seed(seed: int):
 
 def install():
     """Install the shims into sys.modules (idempotent)."""
-    if "vampnet" in sys.modules and getattr(sys.modules["vampnet"], "_is_ref_shim", False):
+    if PKG in sys.modules:
         return
     if not available():
         raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
@@ -104,20 +108,20 @@ def install():
     lora.Linear = _LoraLinear
     sys.modules["loralib"] = lora
 
-    pkg = types.ModuleType("vampnet")
+    pkg = types.ModuleType(PKG)
     pkg.__path__ = [os.path.join(REFERENCE_ROOT, "vampnet")]
     pkg._is_ref_shim = True
-    sys.modules["vampnet"] = pkg
-    mods = types.ModuleType("vampnet.modules")
+    sys.modules[PKG] = pkg
+    mods = types.ModuleType(PKG + ".modules")
     mods.__path__ = [os.path.join(REFERENCE_ROOT, "vampnet", "modules")]
-    sys.modules["vampnet.modules"] = mods
+    sys.modules[PKG + ".modules"] = mods
 
     # vampnet/interface.py:12,16 imports the beat tracker (librosa) and the codec package (lac); neither is in this
     # image and neither is touched by the chunking / masking logic that the Interface tests pin, so both are
     # name-only stubs.
-    beats = types.ModuleType("vampnet.beats")
+    beats = types.ModuleType(PKG + ".beats")
     beats.WaveBeat = type("WaveBeat", (), {})
-    sys.modules["vampnet.beats"] = beats
+    sys.modules[PKG + ".beats"] = beats
     for name in ("lac", "lac.model", "lac.model.lac"):
         if name not in sys.modules:
             m = types.ModuleType(name)
@@ -129,29 +133,27 @@ def install():
 
 
 def uninstall():
+    shim_names = ("audiotools", "audiotools.ml", "audiotools.util", "loralib")
     for k in list(sys.modules):
-        if k == "vampnet" or k.startswith("vampnet.") or k in (
-            "audiotools", "audiotools.ml", "audiotools.util", "loralib", "lac", "lac.model", "lac.model.lac"
-        ):
-            m = sys.modules[k]
-            if k.startswith("vampnet") and not getattr(sys.modules.get("vampnet"), "_is_ref_shim", False):
-                continue
+        if k == PKG or k.startswith(PKG + ".") or k in shim_names:
+            del sys.modules[k]
+        elif k in ("lac", "lac.model", "lac.model.lac") and getattr(sys.modules[k], "_is_ref_shim", False):
             del sys.modules[k]
 
 
 def load_reference():
     """Return (transformer_module, mask_module, util_module) of the reference."""
     install()
-    tr = importlib.import_module("vampnet.modules.transformer")
-    mk = importlib.import_module("vampnet.mask")
-    ut = importlib.import_module("vampnet.util")
+    tr = importlib.import_module(PKG + ".modules.transformer")
+    mk = importlib.import_module(PKG + ".mask")
+    ut = importlib.import_module(PKG + ".util")
     return tr, mk, ut
 
 
 def load_reference_interface():
     """The reference's vampnet/interface.py module (Interface with its own chunking / masking code)."""
     install()
-    return importlib.import_module("vampnet.interface")
+    return importlib.import_module(PKG + ".interface")
 
 
 class StubCodec:
