@@ -86,6 +86,11 @@ void vnb_model_destroy(vnb_model* m);
 int32_t vnb_forward_codes(vnb_model* m, const int64_t* codes, int32_t B, int32_t T, float* logits, void* stream);
 /* VampNet.forward on caller-supplied latents (B, 8C, T) fp32 (transformer.py:617). */
 int32_t vnb_forward_latents(vnb_model* m, const float* latents, int32_t B, int32_t T, float* logits, void* stream);
+/* VampNet.forward(return_activations=True) (transformer.py:617-639, 443-461): as vnb_forward_latents, and the fp32
+ * residual stream after EVERY layer is copied to acts (n_layers, B, T, d_model) — the reference's
+ * torch.stack(activations). */
+int32_t vnb_forward_latents_acts(vnb_model* m, const float* latents, int32_t B, int32_t T, float* logits, float* acts,
+                                 void* stream);
 /* Debug tap: copy the fp32 residual stream (B*T, d) after the last layer of the last forward. */
 int32_t vnb_get_hidden(vnb_model* m, float* out, void* stream);
 
@@ -123,19 +128,6 @@ uint64_t vnb_graph_capture_count(void);
  *              half of the weight tile), 0 = one CTA per 128 x 256 tile.  Results are bit-identical (same
  *              accumulation order per output element).  Initial value: environment VNB_GEMM_PAIR, else the
  *              compiled default.  Generate graphs are cached per value.
- * "resid_tma": epilogue of the residual GEMMs (x += A.W^T, attention output and FFN down) on CTA pairs: 0 = residual
- *              rows staged through registers, 1 = residual tiles moved by TMA (in, update in shared memory, out) for
- *              K <= 1280, 2 = for every residual GEMM.  Bit-identical results.  Initial value: environment
- *              VNB_RESID_TMA, else the compiled default.
- * "pair_arrive_cta": CTA pairs signal "accumulator drained" to the MMA-issuing CTA with a .cta-scope release instead
- *              of .release.cluster (which costs a GPU-scope fence per tile and warp).  0 (default, the measured form)
- *              or 1 (experimental until measured).  Environment VNB_PAIR_ARRIVE_CTA.
- * "attn_p_tmem": attention probabilities go softmax -> tensor memory (tcgen05.st) -> P.V with the A operand read from
- *              TMEM, instead of through 128B-swizzled shared memory and a generic->async proxy fence.  0 (default, the
- *              measured form) or 1 (experimental until measured).  Environment VNB_ATTN_P_TMEM.
- * "attn_v2":     the second attention design (attention2_tcgen05.cu): two 128-query tiles per CTA in ping-pong, 128-key
- *              blocks, one thread per row, P through tensor memory, one-pass optimistic softmax.  0 (default, the
- *              measured first design) or 1 (experimental until measured).  Environment VNB_ATTN_V2.
  * "gemm_pair_max_clusters" (get only): CTA pairs that can be co-resident on the current device. */
 int32_t vnb_set_option(const char* name, int32_t value);
 int32_t vnb_get_option(const char* name, int32_t* value);

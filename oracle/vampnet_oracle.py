@@ -168,13 +168,25 @@ def codebook_unflatten(t: torch.Tensor, n_c: int) -> torch.Tensor:
 # the model
 # --------------------------------------------------------------------------------------
 class OracleVampNet:
-    def __init__(self, cfg: OracleConfig, state_dict: Dict[str, torch.Tensor], mode: str = "fp32"):
+    def __init__(self, cfg: OracleConfig, state_dict: Dict[str, torch.Tensor], mode: str = "fp32",
+                 jitter: float = 0.0, jitter_seed: int = 0):
+        """jitter (bf16 mode only) is a CONDITIONING PROBE, not a numeric mode: every activation is multiplied by
+        (1 + jitter * N(0,1)) right before it is rounded to bf16.  With jitter ~1e-7..1e-6 (the size of fp32
+        accumulation-order differences) the logits move by as much as two correct bf16 implementations differ
+        (tests/test_oracle_conditioning_cpu.py): a relative 1e-7 nudge flips the bf16 rounding of a fraction of the
+        activations, each flip is a 2^-9 relative change, and 20 layers amplify them.  The distance between the
+        probe and the unperturbed oracle is therefore the floor for ANY bf16 implementation that does not share the
+        oracle's exact summation order, and the GPU parity tests are calibrated against it."""
         assert mode in ("fp32", "bf16")
+        assert jitter == 0.0 or mode == "bf16"
         self.cfg = cfg
         self.mode = mode
         self.sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
         q = _bf16 if mode == "bf16" else (lambda x: x)
         self.qa = q  # activation rounding at GEMM inputs
+        if jitter > 0.0:
+            gen = torch.Generator().manual_seed(jitter_seed)
+            self.qa = lambda x: _bf16(x * (1.0 + jitter * torch.randn(x.shape, generator=gen)))
         L = cfg.n_layers
         self.layers = []
         for i in range(L):
@@ -261,26 +273,32 @@ class OracleVampNet:
         return self.qa(p1 * gelu) @ lw["w2"].t()
 
     # ---- A7/A13/A14: VampNet.forward (transformer.py:617-639) ---------------------------
-    def forward(self, latents: torch.Tensor, return_hidden: bool = False) -> torch.Tensor:
-        """latents (B, C*8, T) -> logits (B, V, T*Cp)."""
+    def forward(self, latents: torch.Tensor, return_hidden: bool = False, return_activations: bool = False):
+        """latents (B, C*8, T) -> logits (B, V, T*Cp).  return_activations: also the residual stream after every
+        layer, stacked (L, B, T, d) (transformer.py:443-461, 626-637)."""
         cfg = self.cfg
         B, _, T = latents.shape
         x = torch.einsum("bkt,nk->btn", latents.float(), self.emb_w) + self.emb_b  # Conv1d k=1 (layers.py:162)
         bias = self.position_bias(T)
+        acts = []
         if self.mode == "fp32":
             for lw in self.layers:  # TransformerLayer.forward (transformer.py:314-369); FiLM is identity (d_cond=0)
                 x = x + self.attention(self.rmsnorm(x, lw["norm_1"]), lw, bias)
                 x = x + self.ffn(self.rmsnorm(x, lw["norm_3"]), lw)
+                acts.append(x)
             out = self.rmsnorm(x, self.final_norm) @ self.cls_w.t() + self.cls_b  # (B, T, V*Cp), channel = p*Cp + c
         else:
             inv_rms = lambda t: torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6)
             for lw in self.layers:
                 x = x + self.attention(x, lw, bias, inv_rms(x))
                 x = x + self.ffn(x, lw, inv_rms(x))
+                acts.append(x)
             out = (self.qa(x) @ self.cls_w.t()) * inv_rms(x) + self.cls_b
         Cp, V = cfg.n_predict_codebooks, cfg.vocab_size
         # "b (p c) t -> b p (t c)" (transformer.py:634)
         logits = out.view(B, T, V, Cp).permute(0, 2, 1, 3).reshape(B, V, T * Cp)
+        if return_activations:
+            return logits, torch.stack(acts)
         if return_hidden:
             return logits, x
         return logits

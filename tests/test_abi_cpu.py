@@ -32,9 +32,9 @@ def test_sass_has_blackwell_instructions(built):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", built], capture_output=True, text=True).stdout
     # tcgen05.mma, TMA load, tcgen05.ld; the CTA-pair GEMM: cta_group::2 MMA, pair TMA load, multicast commit;
-    # TMA store (residual epilogue variant); tcgen05.st (attention O rescale / P through TMEM)
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "UTMASTG",
-                     "STTM"):
+    # tcgen05.st (attention: P through TMEM, O rescale) and the P.V MMA with its A operand read from tensor memory
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST", "STTM",
+                     "UTCHMMA tmem["):
         assert mnemonic in sass, mnemonic
 
 
@@ -51,7 +51,7 @@ def test_no_product_import_of_oracle():
 
 def test_options_are_host_state_with_measured_defaults(built):
     """vnb_get_option / vnb_set_option are plain host state (no device call): every documented switch exists, the
-    defaults are the MEASURED configuration (CTA-pair GEMM on, every unmeasured variant off), unknown names fail."""
+    default is the MEASURED configuration (CTA-pair GEMM on); the round-1 experimental switches are gone; unknown names fail."""
     import ctypes as C
     import subprocess
     import sys
@@ -62,14 +62,16 @@ lib.vnb_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
 lib.vnb_set_option.argtypes = [C.c_char_p, C.c_int32]
 lib.vnb_last_error.restype = C.c_char_p
 out = {}
-for name in (b"gemm_pair", b"resid_tma", b"pair_arrive_cta", b"attn_p_tmem", b"attn_v2"):
+for name in (b"gemm_pair",):
     v = C.c_int32(-7)
     assert lib.vnb_get_option(name, C.byref(v)) == 0, name
     out[name.decode()] = v.value
-assert out == {"gemm_pair": 1, "resid_tma": 0, "pair_arrive_cta": 0, "attn_p_tmem": 0, "attn_v2": 0}, out
-assert lib.vnb_set_option(b"resid_tma", 2) == 0
+assert out == {"gemm_pair": 1}, out
+assert lib.vnb_set_option(b"gemm_pair", 0) == 0
 v = C.c_int32()
-lib.vnb_get_option(b"resid_tma", C.byref(v)); assert v.value == 2
+lib.vnb_get_option(b"gemm_pair", C.byref(v)); assert v.value == 0
+for gone in (b"resid_tma", b"pair_arrive_cta", b"attn_p_tmem", b"attn_v2"):   # round-1 experiments: measured, then removed
+    assert lib.vnb_set_option(gone, 1) != 0
 assert lib.vnb_set_option(b"nope", 1) != 0 and b"unknown option" in lib.vnb_last_error()
 print("ok")
 """

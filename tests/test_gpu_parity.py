@@ -2,12 +2,14 @@
 the CPU oracle on the same seeded inputs, and against the committed golden fixtures.
 
 Tolerances (stated here, per the north-star):
-  * integer outputs (tokens, masks) — bit-exact given identical logits;
-  * logits — the kernels compute with bf16 operands / fp32 accumulation, so the target is the oracle's
-    "bf16" mode (same rounding points): |diff| <= 2e-2 abs on logits of std ~0.8 and mean |diff| <= 3e-3
-    (measured 1e-3..2e-3: accumulation order + bf16 re-rounding of intermediates at different boundaries).  The distance to the
-    fp32 reference is reported and bounded separately; the reference's own bf16-autocast GPU path sits
-    5.6e-3 mean / 3.2e-2 max from its fp32 CPU path.
+  * integer outputs (tokens, masks) — bit-exact given identical logits; END-TO-END exactness of greedy decisions
+    wherever the fp32 reference's top-2 margin allows it is in tests/test_gpu_parity_shapes.py;
+  * logits — the kernels compute with bf16 operands / fp32 accumulation, so the target is the oracle's "bf16" mode
+    (same rounding points).  That function is chaotic at the rounding level (tests/test_oracle_conditioning_cpu.py: a
+    relative 1e-7 nudge of the activations moves the logits by 1.4e-2 max / 1.8e-3 mean on these tiny models), so the
+    assertion is "within 1.5x of the oracle's own jitter floor on the same inputs", plus the absolute caps 2e-2 / 3e-3;
+  * the distance to the fp32 reference is bounded separately (0.09 max / 1.2e-2 mean on logits of std ~1); the
+    reference's own bf16-autocast GPU path sits 3.2e-2 max / 5.6e-3 mean from its fp32 CPU path.
 """
 import ctypes as C
 import glob
@@ -58,12 +60,15 @@ def test_forward_vs_oracle_and_golden(golden_dir, tag, cfgd, lora):
     got = model(lat.cuda()).cpu()  # (B, V, S)
     assert got.shape == g["logits"].shape
     ref_bf16 = vo.OracleVampNet(cfg, sd, "bf16").forward(lat)
+    floor = (vo.OracleVampNet(cfg, sd, "bf16", jitter=1e-6, jitter_seed=1).forward(lat) - ref_bf16).abs()
     e = (got - ref_bf16).abs()
-    print(f"[{tag}] vs oracle-bf16: max {e.max():.3e} mean {e.mean():.3e}")
+    print(f"[{tag}] vs oracle-bf16: max {e.max():.3e} mean {e.mean():.3e} (oracle jitter floor: max {floor.max():.3e} "
+          f"mean {floor.mean():.3e})")
     assert e.max() < 2e-2 and e.mean() < 3e-3
+    assert e.mean() <= 1.5 * floor.mean() and e.max() <= 1.5 * floor.max() + 5e-3
     e32 = (got - torch.from_numpy(g["logits"])).abs()
     print(f"[{tag}] vs reference fp32 golden: max {e32.max():.3e} mean {e32.mean():.3e}")
-    assert e32.mean() < 2e-2 and e32.max() < 0.3
+    assert e32.mean() < 1.2e-2 and e32.max() < 0.09
     # codes entry point == from_codes + forward
     got2 = model.forward_codes(torch.from_numpy(g["codes"]).cuda(), codec).permute(0, 2, 1).cpu()
     assert torch.equal(got, got2)
@@ -146,26 +151,6 @@ def test_sample_step_unit_vs_oracle(golden_dir):
     assert (want != (zflat.cpu().numpy() == 1024)).sum() <= 2  # ties at the cut only
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden",
-                                                                "generate_tiny_*_greedy_s*.npz"))))
-def test_generate_greedy_vs_reference_golden(path):
-    """End to end against the reference's own greedy output (fp32 CPU).  bf16 operands can flip an argmax
-    whose fp32 margin is tiny, and a flip cascades through later iterations, so this is an agreement
-    *rate* on a random-init model (worst case for margins), reported rather than required to be 1."""
-    g = np.load(path)
-    cfgd = json.loads(str(g["cfg"]))
-    cfg, sd, model, cb, codec = build(cfgd, seed=int(g["weight_seed"]), lora=bool(int(g["lora"])),
-                                      cb_seed=int(g["codebook_seed"]))
-    kw = json.loads(str(g["kwargs"]))
-    z, mask = torch.from_numpy(g["z"]), torch.from_numpy(g["mask"])
-    got = model.generate(codec, start_tokens=z.cuda(), mask=mask.cuda(), _sampling_steps=int(g["steps"]), seed=5,
-                         return_signal=False, **kw).cpu()
-    agree = (got.numpy() == g["out"]).mean()
-    print(f"{os.path.basename(path)}: token agreement with the fp32 reference {agree:.4f}")
-    assert torch.equal(got[mask == 0], z[mask == 0])
-    assert agree > 0.5
-
-
 def test_full_size_forward_cfg1(golden_dir):
     """BASELINE.json configs[0] shape (random-init coarse, d=1280, 20 layers, T=100, B=1) against the
     reference's fp32 CPU logits."""
@@ -177,7 +162,7 @@ def test_full_size_forward_cfg1(golden_dir):
     e = (got[:, :, ::16] - torch.from_numpy(g["logits_sub"])).abs()
     agree = (got.argmax(1).numpy() == g["argmax"]).mean()
     print(f"full coarse T=100: vs fp32 reference max {e.max():.3e} mean {e.mean():.3e}; argmax agreement {agree:.4f}")
-    assert e.mean() < 2e-2 and agree > 0.9
+    assert e.mean() < 1.2e-2 and e.max() < 0.09 and agree > 0.95
 
 
 def test_cpu_model_raises():
@@ -311,3 +296,43 @@ def test_long_context_forward_T3072():
     e = (got - ref).abs()
     print(f"T=3072: max {e.max():.3e} mean {e.mean():.3e}")
     assert e.max() < 2e-2 and e.mean() < 3e-3
+
+
+def test_return_activations_matches_oracle():
+    """VampNet.forward(return_activations=True) (reference transformer.py:617-639, 443-461; used by
+    scripts/utils/gtzan_embeddings.py:123): logits unchanged, activations = the fp32 residual stream after every layer,
+    the last one equal to the hidden-state tap, each within bf16-operand distance of the oracle's."""
+    cfg, sd, model, cb, codec = build(TINY_COARSE)
+    g = torch.Generator().manual_seed(2)
+    z = torch.randint(0, 1025, (2, cfg.n_codebooks, 50), generator=g)
+    orc = vo.OracleVampNet(cfg, sd, "bf16")
+    lat = orc.from_codes(z, cb)
+    plain = model(lat.cuda()).clone()
+    logits, acts = model(lat.cuda(), return_activations=True)
+    assert torch.equal(logits, plain)
+    assert acts.shape == (cfg.n_layers, 2, 50, cfg.embedding_dim) and acts.dtype == torch.float32
+    assert torch.equal(acts[-1], model.hidden_state(2, 50))
+    _, want = orc.forward(lat, return_activations=True)
+    for layer in range(cfg.n_layers):
+        e = (acts[layer].cpu() - want[layer]).abs()
+        scale = want[layer].abs().mean().item()
+        assert e.max() < 0.05 * max(scale, 1.0) and e.mean() < 5e-3 * max(scale, 1.0), (layer, e.max().item(), scale)
+    assert not torch.equal(acts[0], acts[1])
+
+
+def test_broadcastable_mask_and_flash_checkpoint_rejected():
+    """generate() accepts a (1, C, T) mask against B > 1 start tokens like the reference's masked_fill (:762); a
+    flash_attn=True checkpoint (FlashMHA tensor names) is refused instead of silently leaving random projections."""
+    cfg, sd, model, cb, codec = build(TINY_COARSE)
+    g = torch.Generator().manual_seed(4)
+    z = torch.randint(0, 1024, (3, cfg.n_codebooks, 30), generator=g).cuda()
+    mask = torch.ones(1, cfg.n_codebooks, 30, dtype=torch.long).cuda()
+    mask[:, :, ::3] = 0
+    kw = dict(_sampling_steps=3, seed=2, return_signal=False, sample_cutoff=-1.0, mask_temperature=0.0)
+    a = model.generate(codec, start_tokens=z, mask=mask, **kw)
+    b = model.generate(codec, start_tokens=z, mask=mask.expand(3, -1, -1).contiguous(), **kw)
+    assert torch.equal(a, b)
+    bad = dict(sd)
+    bad["transformer.layers.0.self_attn.Wqkv.weight"] = torch.zeros(3 * cfg.embedding_dim, cfg.embedding_dim)
+    with pytest.raises(RuntimeError, match="FlashMHA"):
+        model.load_state_dict(bad, strict=False)

@@ -45,6 +45,11 @@ def test_forward_and_generate_live(ref_mods, tag, lora):
     with torch.no_grad():
         lr = ref(lat_ref)
     assert (lr - orc.forward(lat_ref)).abs().max() < 3e-5
+    with torch.no_grad():  # return_activations: residual stream after every layer (transformer.py:443-461)
+        lr2, acts_ref = ref(lat_ref, return_activations=True)
+    lo2, acts = orc.forward(lat_ref, return_activations=True)
+    assert acts_ref.shape == acts.shape == (cfg.n_layers, 3, 31, cfg.embedding_dim)
+    assert (acts_ref - acts).abs().max() < 3e-5 * max(1.0, acts_ref.abs().max().item()) and torch.equal(lr2, lr)
     mask = torch.ones_like(z)
     mask[:, :, ::5] = 0
     for kw in (dict(sample_cutoff=-1.0, mask_temperature=0.0), dict(), dict(temperature=1.3, top_p=0.8),

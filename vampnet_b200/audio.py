@@ -137,24 +137,26 @@ class AudioSignal:
             G[3:] = 1.41
         zsum = (z * G[None, :, None]).sum(1)  # (B, nblocks)
         lj = -0.691 + 10 * torch.log10(zsum.clamp_min(1e-12))
-        out = []
-        for b in range(B):
-            keep = lj[b] > -70.0
-            if not keep.any():
-                out.append(torch.tensor(-70.0, device=x.device))
-                continue
-            rel = -0.691 + 10 * torch.log10(zsum[b][keep].mean().clamp_min(1e-12)) - 10.0
-            keep2 = keep & (lj[b] > rel)
-            if not keep2.any():
-                out.append(torch.tensor(-70.0, device=x.device))
-                continue
-            out.append(-0.691 + 10 * torch.log10(zsum[b][keep2].mean().clamp_min(1e-12)))
-        return torch.stack(out).clamp_min(-70.0)
+        # two-stage gating, batched (no per-item loop, no host synchronisation): absolute gate at -70 LUFS, then the
+        # relative gate 10 LU below the mean of the blocks that passed it; items with no block left report -70
+        def gated_mean(keep):
+            n = keep.sum(1)
+            return (zsum * keep).sum(1) / n.clamp_min(1), n
+        keep = lj > -70.0
+        m1, n1 = gated_mean(keep)
+        rel = -0.691 + 10 * torch.log10(m1.clamp_min(1e-12)) - 10.0
+        keep2 = keep & (lj > rel[:, None])
+        m2, n2 = gated_mean(keep2)
+        out = -0.691 + 10 * torch.log10(m2.clamp_min(1e-12))
+        floor = torch.full_like(out, -70.0)
+        return torch.where((n1 > 0) & (n2 > 0), out, floor).clamp_min(-70.0)
 
-    def normalize(self, db: float = -24.0):
-        """Scale to the target integrated loudness."""
+    def normalize(self, db=-24.0):
+        """Scale to the target integrated loudness: a number, or a tensor broadcast over the batch (app.py:248 passes
+        the input's measured loudness, one value, to a batch of generated variations)."""
         ref = self.loudness()
-        gain = torch.exp((float(db) - ref) * math.log(10.0) / 20.0)
+        target = torch.as_tensor(db, dtype=ref.dtype, device=ref.device).reshape(-1)
+        gain = torch.exp((target - ref) * math.log(10.0) / 20.0)
         self.audio_data = self.audio_data * gain[:, None, None]
         return self
 

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvampnet_b200.so")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention2_tcgen05.cu", "elementwise.cu", "sampler.cu", "codec.cu", "conv_tcgen05.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "elementwise.cu", "sampler.cu", "codec.cu", "conv_tcgen05.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 

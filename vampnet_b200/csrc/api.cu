@@ -70,34 +70,6 @@ bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t col
   }
   return true;
 }
-// Row-major (rows, cols) of fp32 (elem_bytes 4) or bf16 (2) with a (box_rows x box_cols) box whose inner extent is
-// exactly the swizzle span (box_cols * elem_bytes == swizzle_bytes, 64 or 128).
-bool make_tmap_2d_ex(CUtensorMap* tm, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                     uint32_t box_cols, int swizzle_bytes) {
-  auto enc = get_encode();
-  if (!enc) return false;
-  if ((elem_bytes != 2 && elem_bytes != 4) || (swizzle_bytes != 64 && swizzle_bytes != 128) ||
-      static_cast<int>(box_cols) * elem_bytes != swizzle_bytes) {
-    g_tmap_err = "make_tmap_2d_ex: unsupported element size / swizzle / box";
-    return false;
-  }
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * static_cast<uint64_t>(elem_bytes)};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    char b[256];
-    snprintf(b, sizeof(b), "cuTensorMapEncodeTiled(2d ex rows=%llu cols=%llu elem=%d box=%ux%u) -> %d",
-             (unsigned long long)rows, (unsigned long long)cols, elem_bytes, box_rows, box_cols, (int)r);
-    g_tmap_err = b;
-    return false;
-  }
-  return true;
-}
 bool make_tmap_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
                   uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols) {
   auto enc = get_encode();
@@ -128,25 +100,14 @@ bool make_gemm_plan(GemmPlan* p, int epi, const void* A, const void* W, int M, i
   }
   p->M = M; p->N = N; p->K = K; p->epi = epi; p->out = out; p->out2 = out2; p->bias = bias;
   p->T = T; p->Tpad = Tpad; p->d2 = d2;
-  memset(&p->tmR, 0, sizeof(p->tmR));
-  memset(&p->tmO, 0, sizeof(p->tmO));
-  p->has_tmR = p->has_tmO = false;
-  if (!(make_tmap_2d(&p->tmA, A, M, K, 128, 64) && make_tmap_2d(&p->tmB, W, N, K, 256, 64) &&
-        make_tmap_2d(&p->tmBh, W, N, K, 128, 64)))
-    return false;
-  if (epi == VNB_EPI_RESID) {  // residual stream tiles for the TMA epilogue: 32 rows x 32 fp32, 128B-swizzled
-    if (!make_tmap_2d_ex(&p->tmR, out, 4, M, N, 32, 32, 128)) return false;
-    p->has_tmR = true;
-  }
-  return true;
+  return make_tmap_2d(&p->tmA, A, M, K, 128, 64) && make_tmap_2d(&p->tmB, W, N, K, 256, 64) &&
+         make_tmap_2d(&p->tmBh, W, N, K, 128, 64);
 }
 
 // RESID plans that also produce the next GEMM's operand: bf16 copy of the updated rows + row sums of squares.
 bool gemm_plan_set_fused_out(GemmPlan* p, void* out_bf16, float* ss_out) {
   p->out_bf16 = out_bf16;
   p->ss_out = ss_out;
-  if (!make_tmap_2d_ex(&p->tmO, out_bf16, 2, p->M, p->N, 32, 32, 64)) return false;
-  p->has_tmO = true;
   return true;
 }
 
@@ -155,7 +116,7 @@ bool make_attn_plan(AttnPlan* p, const void* qk, const void* vT, void* out, cons
   const int d = H * 64;
   p->out = out; p->rel = rel; p->sat = sat; p->B = B; p->T = T; p->Tpad = Tpad; p->H = H;
   return make_tmap_3d(&p->tmQ, qk, B, T, 2 * d, 2 * d, 128, 64) && make_tmap_3d(&p->tmK, qk, B, T, 2 * d, 2 * d, 64, 64) &&
-         make_tmap_3d(&p->tmVT, vT, B, d, Tpad, Tpad, 64, 64) && make_tmap_3d(&p->tmK128, qk, B, T, 2 * d, 2 * d, 128, 64);
+         make_tmap_3d(&p->tmVT, vT, B, d, Tpad, Tpad, 64, 64);
 }
 
 // ---------------------------------------------------------------------------------- model
@@ -176,7 +137,7 @@ struct GraphKey {  // graphs bake pointers, so generate() stages z/mask/out in w
   int steps;
   bool has_mask;
   bool top_p;  // selects the sampler kernel variant
-  int variant;  // GEMM kernel variants baked into the graph (vnb_set_option "gemm_pair", "resid_tma")
+  int variant;  // GEMM kernel variant baked into the graph (vnb_set_option "gemm_pair")
   bool operator<(const GraphKey& o) const {
     return std::tie(steps, has_mask, top_p, variant) < std::tie(o.steps, o.has_mask, o.top_p, o.variant);
   }
@@ -317,7 +278,7 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   } while (0)
 
 // x already holds the embedded input; runs the L layers + final norm + classifier into `logits`.
-static int run_stack(vnb_model* m, Workspace* ws, float* logits, cudaStream_t st) {
+static int run_stack(vnb_model* m, Workspace* ws, float* logits, cudaStream_t st, float* acts = nullptr) {
   const vnb_config& c = m->cfg;
   // RMSNorm (transformer.py:43-58) is fused: norm weights are folded into wqkv / w1 / wcls at pack time, the
   // producers of x (embed, attn-out, ffn-down) also emit bf16(x) and per-row sums of squares, and the consumers
@@ -328,6 +289,8 @@ static int run_stack(vnb_model* m, Workspace* ws, float* logits, cudaStream_t st
     LAUNCH(FAM_GEMM_O, launch_gemm(ws->wo[l], st));
     LAUNCH(FAM_GEMM_UP, launch_gemm(ws->up[l], st));
     LAUNCH(FAM_GEMM_DOWN, launch_gemm(ws->down[l], st));
+    if (acts)  // return_activations: the residual stream after this layer (transformer.py:455-456)
+      CK(cudaMemcpyAsync(acts + static_cast<size_t>(l) * ws->M * c.d_model, ws->x.p, ws->x.n, cudaMemcpyDeviceToDevice, st));
   }
   GemmPlan cls = ws->cls;
   cls.out = logits;
@@ -395,6 +358,18 @@ int32_t vnb_forward_latents(vnb_model* m, const float* latents, int32_t B, int32
   return run_stack(m, ws, logits, st);
 }
 
+int32_t vnb_forward_latents_acts(vnb_model* m, const float* latents, int32_t B, int32_t T, float* logits, float* acts,
+                                 void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Workspace* ws;
+  if (get_workspace(m, B, T, &ws)) return 1;
+  const vnb_config& c = m->cfg;
+  LAUNCH(FAM_EMBED, launch_embed_latents(latents, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), B, T, c.n_codebooks * 8, c.d_model, st,
+                                          ws->y.p, ws->ssA.as<float>(), ws->ss_parts));
+  m->last = ws;
+  return run_stack(m, ws, logits, st, acts);
+}
+
 int32_t vnb_get_hidden(vnb_model* m, float* out, void* stream) {
   if (!m->last) return fail("no forward has run");
   CK(cudaMemcpyAsync(out, m->last->x.p, m->last->x.n, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
@@ -459,7 +434,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   const int64_t* gz = ws->z_in.as<int64_t>();
   const int32_t* gmask = mask ? ws->mask_in.as<int32_t>() : nullptr;
   int64_t* gout = ws->z_out.as<int64_t>();
-  GraphKey key{steps, mask != nullptr, use_top_p, get_attn_v2() * 32 + get_attn_p_tmem() * 16 + get_gemm_pair() * 8 + get_pair_arrive_cta() * 4 + get_resid_tma()};
+  GraphKey key{steps, mask != nullptr, use_top_p, get_gemm_pair()};
   auto it = ws->graphs.find(key);
   if (it == ws->graphs.end()) {
     cudaStream_t cap;
@@ -503,44 +478,12 @@ int32_t vnb_set_option(const char* name, int32_t value) {
     set_gemm_pair(value);
     return 0;
   }
-  if (strcmp(name, "resid_tma") == 0) {
-    set_resid_tma(value);
-    return 0;
-  }
-  if (strcmp(name, "pair_arrive_cta") == 0) {
-    set_pair_arrive_cta(value);
-    return 0;
-  }
-  if (strcmp(name, "attn_p_tmem") == 0) {
-    set_attn_p_tmem(value);
-    return 0;
-  }
-  if (strcmp(name, "attn_v2") == 0) {
-    set_attn_v2(value);
-    return 0;
-  }
   return fail("unknown option '%s'", name);
 }
 int32_t vnb_get_option(const char* name, int32_t* value) {
   if (!name || !value) return fail("null argument");
   if (strcmp(name, "gemm_pair") == 0) {
     *value = get_gemm_pair();
-    return 0;
-  }
-  if (strcmp(name, "resid_tma") == 0) {
-    *value = get_resid_tma();
-    return 0;
-  }
-  if (strcmp(name, "pair_arrive_cta") == 0) {
-    *value = get_pair_arrive_cta();
-    return 0;
-  }
-  if (strcmp(name, "attn_p_tmem") == 0) {
-    *value = get_attn_p_tmem();
-    return 0;
-  }
-  if (strcmp(name, "attn_v2") == 0) {
-    *value = get_attn_v2();
     return 0;
   }
   if (strcmp(name, "gemm_pair_max_clusters") == 0) {  // read-only: co-resident CTA pairs on the current device
@@ -576,8 +519,14 @@ int32_t vnb_sample_step(const float* logits, int32_t* zflat, int32_t* tokens_out
                         int32_t do_sample, float temperature, float gamma, float temp_eff, uint32_t seed_lo,
                         uint32_t seed_hi, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static SampleDyn* scratch = nullptr;
-  static int slot = 0;
+  // per-device ring of parameter slots (a process-global one would live on whichever device called first)
+  static SampleDyn* scratch_dev[64] = {nullptr};
+  static int slot_dev[64] = {0};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail("device index %d out of range", dev);
+  SampleDyn*& scratch = scratch_dev[dev];
+  int& slot = slot_dev[dev];
   if (!scratch) CK(cudaMalloc(&scratch, sizeof(SampleDyn) * 64));
   SampleDyn d;
   d.inv_temp = temperature > 0.f ? static_cast<float>(1.0 / static_cast<double>(temperature)) : 1.0f;

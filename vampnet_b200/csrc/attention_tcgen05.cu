@@ -1,109 +1,204 @@
-// vampnet_b200 — fused bidirectional self-attention with T5-style relative-position bias on the
-// sm_100a tensor cores.
+// vampnet_b200 — fused bidirectional self-attention with T5-style relative-position bias on the sm_100a tensor cores.
 //
-// Replaces MultiHeadRelativeAttention.forward between the projections (reference
-// vampnet/modules/transformer.py:234-254): scores = q.k^T / sqrt(64) + bias[h, k - q]; softmax over
-// keys; out = P.v; heads merged as "b l (head v)".  The reference materialises (H,B,T,T) scores in
-// HBM three times per layer; here they live only in TMEM/registers.  The position bias
-// (compute_bias, :183-209) is Toeplitz in (k - q) and saturates beyond |k - q| >= sat, so it is a
+// Replaces MultiHeadRelativeAttention.forward between the projections (reference vampnet/modules/transformer.py:234-254):
+// scores = q.k^T / sqrt(64) + bias[h, k - q]; softmax over keys; out = P.v; heads merged as "b l (head v)".  The
+// reference materialises (H,B,T,T) scores in HBM three times per layer; here they live only in TMEM / registers.  The
+// position bias (compute_bias, :183-209) is Toeplitz in (k - q) and saturates beyond |k - q| >= sat, so it is a
 // (2*sat+1)-entry table per head held in shared memory.
 //
-// One CTA = one (batch, head, 128-query tile); key/value blocks of 64:
+// One CTA = (batch, head, 128 queries), 64-key blocks, two CTAs per SM (256 TMEM columns each: S[2] | O | P[2]):
 //   warp 0      TMA producer (Q once; K_j and V^T_j through a 3-stage ring); owns the TMEM allocation
-//   warp 1      MMA issuer   S[j&1] = Q.K_j^T (tcgen05.mma M128 N64 K16 x4), issued one block AHEAD of the
-//                            softmax into a double-buffered TMEM score tile ; O += P_j.V_j (same shape) from a
-//                            double-buffered P tile, so softmax(j+1) never waits for P.V(j)
-//   warps 2..9  softmax      two threads per query row (32 keys each): tcgen05.ld S -> scale+bias -> row max ->
-//                            exp2 -> bf16 P into 128B-swizzled smem (A operand of P.V) ; O stays in TMEM
-//                            and is rescaled in place only when a row's reference max grows by > 2^8
-//                            (lazy rescale: P may exceed 1 by that factor, harmless in bf16/fp32).
-// Roofline: tensor-bound in FLOPs (4*T^2*64 per (b,h)), but at d_head = 64 the per-block TMEM read
-// (128x64 fp32) and MUFU.EX2 cost as much as the two MMAs; see DESIGN.md.
+//   warp 1      MMA issuer: S[j&1] = Q.K_j^T two blocks ahead of the softmax; O += P_j.V_j with the A operand (P) read
+//               from TENSOR memory (tcgen05.mma A-from-TMEM: no shared-memory store of P, no generic->async proxy fence)
+//   warps 2..9  softmax, two threads per query row (32 keys of every block each), ONE pass per block:
+//               tcgen05.ld S -> FFMA2 (scale, bias and the reference max folded into one packed multiply-add) -> exp2
+//               -> row sum -> bf16 pack -> tcgen05.st P.  The exponentials (MUFU, the binding unit at d_head 64:
+//               512 MUFU cycles against 256 tensor cycles per 128 x 64 tile) and the FMA/ALU work sit in the same
+//               straight-line loop, so they overlap inside every warp; nothing but 32 raw scores and the packed P
+//               is live, so the addresses and loop state stay in registers (an earlier two-phase version kept 64
+//               logits per thread and executed ~3 rematerialised integer instructions per useful one).
+// The softmax is OPTIMISTIC: P is computed against the running reference max m_ref (set by a max-only pre-pass over
+// block 0) while the block maximum is tracked on the side; the two threads of a row exchange it through shared memory
+// once per block, and only when a row grew by more than 2^8 is the reference moved, O and l rescaled and the block's P
+// recomputed from the score tile (still in TMEM: it is released together with P).
+//
+// Measured on B200 at B=32, T=768, H=20 (profiles/attention_r2_variants.txt): this kernel 198 us (489 TFLOP/s); the round-1
+// kernel (two-phase, P through shared memory) 222 us; P through TMEM alone 205 us; two 128-query tiles per CTA with
+// 128-key blocks 240-258 us; evaluating 25-50 % of the exponentials as a cubic polynomial on the FMA pipe did not help
+// in any of them (the kernels are issue/latency-bound at 20 warps per SM, not MUFU-bound), so that path was removed.
 #include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vnb {
+namespace att {
 
-constexpr int AQ = 128, AK = 64, DH = 64;
-constexpr int KV_STAGES = 3;
-constexpr int Q_BYTES = AQ * DH * 2;   // 16 KiB
-constexpr int K_BYTES = AK * DH * 2;   // 8 KiB
-constexpr int V_BYTES = DH * AK * 2;   // 8 KiB
-constexpr int P_BYTES = AQ * AK * 2;   // 16 KiB
-constexpr int ATT_MAX_SAT = 128;
-constexpr int ATT_PAD = 160;  // a lookup block spans 128 query rows + 32 keys: pad the table so indices never clamp
-constexpr int ATT_TAB = 2 * (ATT_MAX_SAT + ATT_PAD) + 2;
-constexpr int ATT_SMEM_TILES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES;  // 96 KiB (P double buffered)
-constexpr int ATT_SMEM = ATT_SMEM_TILES + 1024 /*align*/ + ATT_TAB * 4 + 2 * 2 * AQ * 4 /*row-max exchange*/ +
-                         256 /*barriers*/;
-constexpr int ATT_THREADS = 320;  // producer + MMA + 8 softmax warps (two threads per query row)
+constexpr int AQ = 128, AK = 64, DH = 64, KV_STAGES = 3;
+constexpr int Q_BYTES = AQ * DH * 2;        // 16 KiB
+constexpr int K_BYTES = AK * DH * 2;        // 8 KiB
+constexpr int V_BYTES = DH * AK * 2;        // 8 KiB
+constexpr int MAX_SAT = 128;
+constexpr int PAD = 64;                     // a lookup chunk is 32 rows x 32 keys: |rel| < sat + 62
+constexpr int TAB = 2 * (MAX_SAT + PAD) + 2;
+constexpr int THREADS = 320;
+constexpr int XCH = 2 /*slot*/ * 2 /*half*/ * AQ;   // row-max / row-sum exchange, floats
+constexpr int SMEM = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + TAB * 4 + XCH * 4 + 256;
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 domain: O is rescaled only when a row max grows by > 2^8
+constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 domain
 
-struct AttnArgs {
+struct Args {
   __nv_bfloat16* out;
   const float* rel;
   int sat, B, T, H, d;
 };
 
-// Half a 64-key block (32 keys) of one query row: turn raw scores (TMEM) into exp2-domain logits, return the
-// max over these 32.  Scale+bias runs as packed FFMA2 (two keys per issue slot).
-template <bool TAIL, bool LOOKUP>
-__device__ __forceinline__ float scores_to_logits(uint32_t (&sr)[32], float c, float bconst, uint32_t bias_addr,
-                                                  int valid) {
-  float mx = -INFINITY;
-  const uint64_t c2 = pack2(c, c);
-  const uint64_t b2c = pack2(bconst, bconst);
+// One pass over this thread's 32 keys of a block: t' = score * c + bias - m_ref (exp2 domain; keys beyond T -> -inf),
+// block maximum of t', and (DO_EXP) P = exp2(t'), row sum, bf16 pack.  Constant-bias chunks take bias - m_ref as one
+// scalar, so scale + bias + reference are a single packed FFMA2 per pair of keys.
+template <bool TAIL, bool LOOKUP, bool DO_EXP>
+__device__ __forceinline__ float chunk_pass(const uint32_t (&s)[32], uint32_t (&pk)[16], uint64_t (&psum2)[2], float c,
+                                            float add, float m_ref, uint32_t bias_addr, int valid) {
+  float mx[2] = {-INFINITY, -INFINITY};
+  const uint64_t c2 = pack2(c, c), a2 = pack2(add, add), nm2 = pack2(-m_ref, -m_ref);
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    uint64_t b2 = b2c;
-    if constexpr (LOOKUP) b2 = pack2(lds_f32(bias_addr + 4 * i), lds_f32(bias_addr + 4 * i + 4));
-    const uint64_t t2 = ffma2(pack2(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])), c2, b2);
+  for (int i = 0; i < 16; ++i) {
+    uint64_t t2;
+    const uint64_t s2 = pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+    if constexpr (LOOKUP) {
+      const uint64_t b2 = pack2(lds_f32(bias_addr + 8 * i), lds_f32(bias_addr + 8 * i + 4));
+      t2 = fadd2(ffma2(s2, c2, b2), nm2);
+    } else {
+      t2 = ffma2(s2, c2, a2);
+    }
     float t0, t1;
     unpack2(t2, t0, t1);
     if constexpr (TAIL) {
-      if (i >= valid) t0 = -INFINITY;
-      if (i + 1 >= valid) t1 = -INFINITY;
+      if (2 * i >= valid) t0 = -INFINITY;
+      if (2 * i + 1 >= valid) t1 = -INFINITY;
     }
-    sr[i] = __float_as_uint(t0);
-    sr[i + 1] = __float_as_uint(t1);
-    mx = fmaxf(mx, fmaxf(t0, t1));
+    mx[i & 1] = fmaxf(mx[i & 1], fmaxf(t0, t1));
+    if constexpr (DO_EXP) {
+      const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
+      psum2[i & 1] = fadd2(psum2[i & 1], pack2(p0, p1));
+      pk[i] = pack_bf16x2(p0, p1);
+    }
   }
-  return mx;
+  return fmaxf(mx[0], mx[1]);
 }
 
-__device__ __forceinline__ void pair_barrier(int id) {  // the two warps that share a TMEM lane quadrant
-  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// PTMEM = true (option "attn_p_tmem", experimental): the probabilities never touch shared memory.  Each softmax thread
-// writes its 32 bf16 P values into tensor memory (tcgen05.st, columns [192,256): two 128 x 64 bf16 tiles) and P.V is
-// issued with the A operand read from TMEM.  This removes the 8 x STS.128 per thread and block, the shared-memory
-// reads of P by the tensor core, and the generic->async proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: 14 % of the
-// kernel's stall samples under ncu, profiles/ncu_attn_r1_final.txt / DESIGN.md §8).
-template <bool PTMEM>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+// shared-memory map, byte offsets from the 1024-aligned base (every address below is base + constant)
+constexpr uint32_t OFF_Q = 0;
+constexpr uint32_t OFF_K = OFF_Q + Q_BYTES;
+constexpr uint32_t OFF_V = OFF_K + KV_STAGES * K_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_V + KV_STAGES * V_BYTES;
+constexpr uint32_t OFF_X = OFF_BIAS + TAB * 4;           // [slot][half][128 rows] floats
+constexpr uint32_t OFF_BAR = (OFF_X + XCH * 4 + 7) & ~7u;
+constexpr uint32_t BAR_Q_FULL = OFF_BAR;
+constexpr uint32_t BAR_KV_FULL = OFF_BAR + 8;                      // [KV_STAGES]
+constexpr uint32_t BAR_KV_EMPTY = BAR_KV_FULL + 8 * KV_STAGES;     // [KV_STAGES]
+constexpr uint32_t BAR_S_FULL = BAR_KV_EMPTY + 8 * KV_STAGES;      // [2] S[j&1] = Q.K_j^T complete
+constexpr uint32_t BAR_P_FULL = BAR_S_FULL + 16;                   // [2] P[j&1] written, S[j&1] consumed (256 arrivals)
+constexpr uint32_t BAR_P_FREE = BAR_P_FULL + 16;                   // [2] P.V of block j retired
+constexpr uint32_t OFF_TMEM_SLOT = BAR_P_FREE + 16;
+static_assert(OFF_TMEM_SLOT + 16 <= SMEM, "shared-memory map exceeds the allocation");
+
+
+// Per-thread state of a softmax thread (all members live in registers: every method is force-inlined).
+struct Softmax {
+  static constexpr uint32_t X_SLOT = 2 * AQ * 4;    // bytes between the two exchange slots
+  uint32_t sb, tS, tO, tP, x_own, x_par;
+  float bias_lo, bias_hi, m_ref, l;
+  int pair_bar, kq_row, kq_warp, koff, sat, T, nblk;
+  uint64_t psum2[2];
+
+  // dispatch on the bias regime / tail of this warp's 32 x 32 patch of block j
+  template <bool DO_EXP>
+  __device__ __forceinline__ float pass(int j, const uint32_t (&sn)[32], uint32_t (&pk)[16]) {
+    const float c = 0.125f * LOG2E;                             // 1/sqrt(64) folded with log2(e)
+    const int rel0 = j * AK + kq_warp;                          // key - query at the patch's (first key, first row)
+    const bool hi = rel0 - 31 >= sat;
+    const bool is_const = hi || (rel0 + 31 <= -sat);
+    const int valid = T - (j * AK + koff);
+    const bool tail = valid < 32;
+    const float add = (hi ? bias_hi : bias_lo) - m_ref;
+    const uint32_t bias_addr = sb + OFF_BIAS + 4u * static_cast<uint32_t>(j * AK + kq_row + sat + PAD);
+    if (is_const)
+      return tail ? chunk_pass<true, false, DO_EXP>(sn, pk, psum2, c, add, m_ref, bias_addr, valid)
+                  : chunk_pass<false, false, DO_EXP>(sn, pk, psum2, c, add, m_ref, bias_addr, valid);
+    return tail ? chunk_pass<true, true, DO_EXP>(sn, pk, psum2, c, add, m_ref, bias_addr, valid)
+                : chunk_pass<false, true, DO_EXP>(sn, pk, psum2, c, add, m_ref, bias_addr, valid);
+  }
+  // maximum over both threads of the row (one 64-thread named barrier)
+  __device__ __forceinline__ float row_max(int use, float mx) {
+    const uint32_t slot = static_cast<uint32_t>(use & 1) * X_SLOT;
+    sts_f32(x_own + slot, mx);
+    named_barrier(pair_bar, 64);
+    return fmaxf(mx, lds_f32(x_par + slot));
+  }
+  __device__ __forceinline__ void load_scores(int j, uint32_t (&sn)[32]) {
+    tmem_ld_x32(tS + static_cast<uint32_t>(j & 1) * 64, sn);
+    tmem_wait_ld();
+  }
+  __device__ __forceinline__ void block(int j) {
+    const uint32_t jb = static_cast<uint32_t>(j & 1);
+    uint32_t sn[32], pk[16];
+    mbar_wait_a(sb + BAR_S_FULL + 8 * jb, (j >> 1) & 1, 740);
+    tc_fence_after();
+    load_scores(j, sn);
+    if (j == 0) {  // no reference yet: a max-only pass over block 0 sets it (use 0 of the exchange slots)
+      m_ref = row_max(0, pass<false>(0, sn, pk));
+    }
+    if (j >= 2) {  // P[j&1] was last read by the P.V of block j-2 (long retired)
+      mbar_wait_a(sb + BAR_P_FREE + 8 * jb, ((j - 2) >> 1) & 1, 755);
+      tc_fence_after();
+    }
+    psum2[0] = pack2(0.f, 0.f);
+    psum2[1] = pack2(0.f, 0.f);
+    const float mx = row_max(j + 1, pass<true>(j, sn, pk));
+    const float delta = mx > RESCALE_THRESHOLD ? mx : 0.f;
+    if (__any_sync(0xffffffffu, delta != 0.f)) {
+      // rare: some row of this warp outgrew its reference by more than 2^8.  Move the reference, rescale O and l
+      // (every P.V issued so far must have retired) and recompute this block's P from the score tile in TMEM.
+      m_ref += delta;
+      if (j > 0) {
+        mbar_wait_a(sb + BAR_P_FREE + 8 * (jb ^ 1u), ((j - 1) >> 1) & 1, 750);
+        tc_fence_after();
+        const float alpha = fast_exp2(-delta);             // exactly 1 for rows that keep their reference
+        uint32_t o[32];
+        tmem_ld_x32(tO, o);                                // each half rescales its own 32 output columns
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_x32(tO, o);
+        tmem_wait_st();
+        l *= alpha;
+      }
+      load_scores(j, sn);
+      psum2[0] = pack2(0.f, 0.f);
+      psum2[1] = pack2(0.f, 0.f);
+      pass<true>(j, sn, pk);
+    }
+    tmem_st_x16(tP + jb * 32, pk);  // keys [32 half, 32 half + 32) of block j -> bf16 pairs in 16 columns
+    float ps0, ps1, ps2, ps3;
+    unpack2(psum2[0], ps0, ps1);
+    unpack2(psum2[1], ps2, ps3);
+    l += (ps0 + ps1) + (ps2 + ps3);
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive_a(sb + BAR_P_FULL + 8 * jb);
+  }
+};
+
+__global__ void __launch_bounds__(THREADS, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                         const __grid_constant__ CUtensorMap tmVT, const AttnArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;                  // KV_STAGES stages
-  uint8_t* sV = sK + KV_STAGES * K_BYTES;      // KV_STAGES stages
-  uint8_t* sP = sV + KV_STAGES * V_BYTES;
-  float* sBias = reinterpret_cast<float*>(sP + 2 * P_BYTES);
-  float* sMx = sBias + ATT_TAB;  // [2 buffers][2 halves][128 rows] row-max / row-sum exchange
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMx + 2 * 2 * AQ);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;                    // [KV_STAGES]
-  uint64_t* kv_empty = kv_full + KV_STAGES;        // [KV_STAGES]
-  uint64_t* s_full = kv_empty + KV_STAGES;         // [2]
-  uint64_t* p_full = s_full + 2;                   // [2] P buffer written (per buffer: a lagging MMA thread can
-                                                   //     never fall two phases behind on the same barrier)
-  uint64_t* p_free = p_full + 2;                   // [2] P buffer consumed by its P.V (also: O updated)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
+                  const __grid_constant__ CUtensorMap tmVT, const Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need the 1024-byte alignment
+  const uint32_t sb = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,17 +208,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int nblk = (a.T + AK - 1) / AK;
 
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
+    mbar_init_a(sb + BAR_Q_FULL, 1);
     for (int s = 0; s < KV_STAGES; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init_a(sb + BAR_KV_FULL + 8 * s, 1);
+      mbar_init_a(sb + BAR_KV_EMPTY + 8 * s, 1);
     }
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_init(&p_full[0], 256);
-    mbar_init(&p_full[1], 256);
-    mbar_init(&p_free[0], 1);
-    mbar_init(&p_free[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init_a(sb + BAR_S_FULL + 8 * i, 1);
+      mbar_init_a(sb + BAR_P_FULL + 8 * i, 2 * AQ);
+      mbar_init_a(sb + BAR_P_FREE + 8 * i, 1);
+    }
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -133,203 +227,123 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tma_prefetch_desc(&tmVT);
     }
     __syncwarp();
-    tmem_alloc<256>(tmem_slot);
-  }
-  // bias table for this head, pre-multiplied by log2(e)
-  // entry [rel + sat + ATT_PAD] for rel in [-(sat+PAD), sat+PAD], saturated outside [-sat, sat]
-  for (int i = threadIdx.x; i < 2 * (a.sat + ATT_PAD) + 1; i += ATT_THREADS) {
-    int r = i - ATT_PAD;
-    r = r < 0 ? 0 : (r > 2 * a.sat ? 2 * a.sat : r);
-    sBias[i] = a.rel[r * a.H + h] * LOG2E;
+    tmem_alloc<256>(reinterpret_cast<uint32_t*>(smem + OFF_TMEM_SLOT));
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;         // two score buffers: columns [0,64) and [64,128)
-  const uint32_t tmem_O = tmem_base + 128;   // columns [128, 192)
-  const uint32_t tmem_P = tmem_base + 192;   // PTMEM: two bf16 P tiles, 32 columns each
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM_SLOT);
+  const uint32_t tmem_S = tmem_base;          // two score buffers: columns [0,64) and [64,128)
+  const uint32_t tmem_O = tmem_base + 128;    // columns [128, 192)
+  const uint32_t tmem_P = tmem_base + 192;    // two bf16 P tiles, 32 columns each
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(q_full, Q_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, h * DH, q0, b);
+      mbar_expect_tx_a(sb + BAR_Q_FULL, Q_BYTES);
+      tma_load_3d_a(sb + OFF_Q, &tmQ, sb + BAR_Q_FULL, h * DH, q0, b);
       for (int j = 0; j < nblk; ++j) {
         const int st = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
-        mbar_wait(&kv_empty[st], ph ^ 1, 500 + st);
-        mbar_expect_tx(&kv_full[st], K_BYTES + V_BYTES);
-        tma_load_3d(sK + st * K_BYTES, &tmK, &kv_full[st], a.d + h * DH, j * AK, b);
-        tma_load_3d(sV + st * V_BYTES, &tmVT, &kv_full[st], j * AK, h * DH, b);
+        mbar_wait_a(sb + BAR_KV_EMPTY + 8 * st, ph ^ 1, 700 + st);
+        mbar_expect_tx_a(sb + BAR_KV_FULL + 8 * st, K_BYTES + V_BYTES);
+        tma_load_3d_a(sb + OFF_K + st * K_BYTES, &tmK, sb + BAR_KV_FULL + 8 * st, a.d + h * DH, j * AK, b);
+        tma_load_3d_a(sb + OFF_V + st * V_BYTES, &tmVT, sb + BAR_KV_FULL + 8 * st, j * AK, h * DH, b);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(AQ, AK);  // M=128, N=64 for both products
-      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      auto issue_qk = [&](int j) {  // S[j&1] = Q . K_j^T, one block ahead of the softmax
+      auto issue_qk = [&](int j) {  // S[j&1] = Q . K_j^T
         const int st = j % KV_STAGES;
-        mbar_wait(&kv_full[st], (j / KV_STAGES) & 1, 510 + st);
+        mbar_wait_a(sb + BAR_KV_FULL + 8 * st, (j / KV_STAGES) & 1, 710 + st);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sK + st * K_BYTES);
-        const uint32_t dS = tmem_S + (j & 1) * 64;
+        const uint32_t aK = sb + OFF_K + st * K_BYTES;
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          umma_bf16(dS, umma_desc_sw128(aQ + k * 32), umma_desc_sw128(aK + k * 32), idesc, k != 0);
-        umma_commit(&s_full[j & 1]);
+          umma_bf16(tmem_S + (j & 1) * 64, umma_desc_sw128(sb + OFF_Q + k * 32), umma_desc_sw128(aK + k * 32), idesc, k != 0);
+        umma_commit_a(sb + BAR_S_FULL + 8 * (j & 1));
       };
-      mbar_wait(q_full, 0, 509);
+      mbar_wait_a(sb + BAR_Q_FULL, 0, 709);
       issue_qk(0);
       if (nblk > 1) issue_qk(1);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j % KV_STAGES;
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1, 520);  // P_j is in smem, S[j&1] has been consumed
+        mbar_wait_a(sb + BAR_P_FULL + 8 * (j & 1), (j >> 1) & 1, 720);   // P_j is in TMEM, S[j&1] has been consumed
         tc_fence_after();
-        const uint32_t aV = smem_u32(sV + st * V_BYTES);
-        const uint32_t aPj = aP + (j & 1) * P_BYTES;
+        const uint32_t aV = sb + OFF_V + (j % KV_STAGES) * V_BYTES;
 #pragma unroll
-        for (int k = 0; k < AK / 16; ++k) {
-          if constexpr (PTMEM)  // 16 keys = 8 columns of bf16 pairs
-            umma_bf16_ts(tmem_O, tmem_P + (j & 1) * 32 + k * 8, umma_desc_sw128(aV + k * 32), idesc, (j | k) != 0);
-          else
-            umma_bf16(tmem_O, umma_desc_sw128(aPj + k * 32), umma_desc_sw128(aV + k * 32), idesc, (j | k) != 0);
-        }
-        umma_commit(&kv_empty[st]);
-        umma_commit(&p_free[j & 1]);
+        for (int k = 0; k < AK / 16; ++k)  // 16 keys = 8 TMEM columns of bf16 pairs
+          umma_bf16_ts(tmem_O, tmem_P + (j & 1) * 32 + k * 8, umma_desc_sw128(aV + k * 32), idesc, (j | k) != 0);
+        umma_commit_a(sb + BAR_KV_EMPTY + 8 * (j % KV_STAGES));
+        umma_commit_a(sb + BAR_P_FREE + 8 * (j & 1));
         if (j + 2 < nblk) issue_qk(j + 2);
       }
     }
   } else {
-    // ===================== softmax warps: two threads per query row (32 keys of each block each) ==========
-    const int quad = warp & 3;                 // TMEM lane quadrant of this warp
-    const int half = (warp - 2) >> 2;          // 0: keys [0,32) of the block, 1: keys [32,64)
+    // ===================== softmax: two threads per query row, 32 keys of every block each =====================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
-    const int q = q0 + row;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const float c = 0.125f * LOG2E;  // 1/sqrt(64) folded with log2(e)
     const int sat = a.sat;
-    float m_ref = -INFINITY, l = 0.f;
-    const int sw = row & 7;
-    const uint32_t sBias_addr = smem_u32(sBias), sMx_addr = smem_u32(sMx), sP_addr = smem_u32(sP);
-    const float bias_lo = sBias[0], bias_hi = sBias[2 * (sat + ATT_PAD)];
-
-    for (int j = 0; j < nblk; ++j) {
-      const int k0 = j * AK + half * 32;
-      const uint32_t prow = sP_addr + (j & 1) * P_BYTES + row * 128;
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1, 540 + (j & 1));
-      tc_fence_after();
-      uint32_t sr[32];
-      tmem_ld_x32(tmem_S + (j & 1) * 64 + half * 32 + lane_off, sr);
-      tmem_wait_ld();
-      // scale + bias (+ mask of keys beyond T), all in the log2 domain
-      // key - query range of THIS WARP's 32 rows x 32 keys: beyond +-sat the bias is one constant
-      const int qw = q0 + quad * 32;
-      const int rel_lo = k0 - (qw + 31), rel_hi = k0 + 31 - qw;
-      const bool is_const = (rel_lo >= sat) || (rel_hi <= -sat);
-      const bool tail = k0 + 32 > a.T;
-      const float bconst = rel_lo >= sat ? bias_hi : bias_lo;
-      // lookup blocks satisfy |k0 - q0| < sat + 160, so rel + sat + ATT_PAD stays inside the padded table
-      const uint32_t bias_addr = sBias_addr + 4u * static_cast<uint32_t>(k0 - q + sat + ATT_PAD);
-      const int valid = a.T - k0;
-      float mx;
-      if (is_const) {
-        mx = tail ? scores_to_logits<true, false>(sr, c, bconst, bias_addr, valid)
-                  : scores_to_logits<false, false>(sr, c, bconst, bias_addr, valid);
-      } else {
-        mx = tail ? scores_to_logits<true, true>(sr, c, bconst, bias_addr, valid)
-                  : scores_to_logits<false, true>(sr, c, bconst, bias_addr, valid);
-      }
-      // row max over both halves (partner = same lane of warp +-4)
-      const uint32_t ex = sMx_addr + static_cast<uint32_t>((j & 1) * 2 * AQ) * 4u;
-      sts_f32(ex + (half * AQ + row) * 4u, mx);
-      pair_barrier(1 + quad);
-      mx = fmaxf(mx, lds_f32(ex + ((half ^ 1) * AQ + row) * 4u));
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        const bool grow = mx > m_ref + RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, grow)) {
-          // rare: O must be stable, i.e. the P.V of the previous block has retired
-          mbar_wait(&p_free[(j - 1) & 1], ((j - 1) >> 1) & 1, 550);
-          tc_fence_after();
-          const float m_new = grow ? mx : m_ref;
-          const float alpha = fast_exp2(m_ref - m_new);  // exactly 1 for rows that keep their reference
-          uint32_t o[32];
-          tmem_ld_x32(tmem_O + lane_off + half * 32, o);  // each half rescales its own 32 output columns
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_x32(tmem_O + lane_off + half * 32, o);
-          tmem_wait_st();
-          l *= alpha;
-          m_ref = m_new;
-        }
-      }
-      // this block's P buffer was last read by the P.V of block j-2
-      if (j >= 2) mbar_wait(&p_free[j & 1], ((j - 2) >> 1) & 1, 555);
-      uint64_t psum2 = pack2(0.f, 0.f);
-      const uint64_t negm2 = pack2(-m_ref, -m_ref);
-      [[maybe_unused]] uint32_t pall[16];
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint64_t d2 = fadd2(pack2(__uint_as_float(sr[ch * 8 + 2 * i]), __uint_as_float(sr[ch * 8 + 2 * i + 1])), negm2);
-          float d0, d1;
-          unpack2(d2, d0, d1);
-          const float p0 = fast_exp2(d0), p1 = fast_exp2(d1);
-          psum2 = fadd2(psum2, pack2(p0, p1));
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        if constexpr (PTMEM) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pall[ch * 4 + i] = pk[i];
-        } else {
-          sts_v4(prow + (((half * 4 + ch) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
-        }
-      }
-      float ps0, ps1;
-      unpack2(psum2, ps0, ps1);
-      l += ps0 + ps1;
-      if constexpr (PTMEM) {
-        // keys [half*32, half*32+32) of this row -> columns [half*16, half*16+16) of the P tile
-        tmem_st_x16(tmem_P + (j & 1) * 32 + half * 16 + lane_off, pall);
-        tmem_wait_st();
-      } else {
-        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      }
-      tc_fence_before();
-      mbar_arrive(&p_full[j & 1]);
-    }
-    // ---- finalize: O / l -> bf16 -> (B, T, d) at [b, q, h*64 + half*32 ..]
+    const int T = a.T;
+    // bias table of this head, times log2(e): entry [rel + sat + PAD], saturated outside [-sat, sat].  Filled by the
+    // softmax warps only (the producer / MMA warps are already loading and multiplying).
     {
-      const uint32_t ex = sMx_addr + static_cast<uint32_t>((nblk & 1) * 2 * AQ) * 4u;
-      sts_f32(ex + (half * AQ + row) * 4u, l);
-      pair_barrier(1 + quad);
-      l += lds_f32(ex + ((half ^ 1) * AQ + row) * 4u);
+      float* sBias = reinterpret_cast<float*>(smem + OFF_BIAS);
+      for (int i = threadIdx.x - 64; i < 2 * (sat + PAD) + 1; i += THREADS - 64) {
+        int r = i - PAD;
+        r = r < 0 ? 0 : (r > 2 * sat ? 2 * sat : r);
+        sBias[i] = a.rel[r * a.H + h] * LOG2E;
+      }
     }
-    mbar_wait(&p_free[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1, 560);
+    named_barrier(9, THREADS - 64);
+    Softmax sm;
+    sm.sb = sb;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    sm.tS = tmem_S + half * 32 + lane_off;
+    sm.tO = tmem_O + half * 32 + lane_off;
+    sm.tP = tmem_P + half * 16 + lane_off;
+    sm.bias_lo = lds_f32(sb + OFF_BIAS);
+    sm.bias_hi = lds_f32(sb + OFF_BIAS + 8 * (sat + PAD));
+    sm.x_own = sb + OFF_X + 4u * static_cast<uint32_t>(half * AQ + row);
+    sm.x_par = sb + OFF_X + 4u * static_cast<uint32_t>((half ^ 1) * AQ + row);
+    sm.pair_bar = 1 + quad;                    // the two warps that share these 32 rows
+    sm.kq_row = half * 32 - (q0 + row);
+    sm.kq_warp = half * 32 - (q0 + quad * 32);
+    sm.koff = half * 32;
+    sm.sat = sat; sm.T = T; sm.nblk = nblk;
+    sm.m_ref = 0.f; sm.l = 0.f;
+    for (int j = 0; j < nblk; ++j) sm.block(j);
+    float l = sm.l;
+    const uint32_t x_own = sm.x_own, x_par = sm.x_par, tO = sm.tO;
+    const int pair_bar = sm.pair_bar;
+    constexpr uint32_t X_SLOT = 2 * AQ * 4;
+    // ---- finalize: O / l -> bf16 -> (B, T, d) at [b, q, h*64 + half*32 ..]
+    {  // exchange use number nblk + 1 (uses 0 .. nblk were the block maxima)
+      const uint32_t slot = static_cast<uint32_t>((nblk + 1) & 1) * X_SLOT;
+      sts_f32(x_own + slot, l);
+      named_barrier(pair_bar, 64);
+      l += lds_f32(x_par + slot);
+    }
+    mbar_wait_a(sb + BAR_P_FREE + 8 * ((nblk - 1) & 1), ((nblk - 1) >> 1) & 1, 760);
     tc_fence_after();
     const float inv_l = 1.0f / l;
-    __nv_bfloat16* orow = a.out + (static_cast<size_t>(b) * a.T + q) * a.d + h * DH + half * 32;
-    {
-      uint32_t o[32];
-      tmem_ld_x32(tmem_O + lane_off + half * 32, o);
-      tmem_wait_ld();
-      if (q < a.T) {
-        uint4* o4 = reinterpret_cast<uint4*>(orow);
+    const int q = q0 + row;
+    __nv_bfloat16* orow = a.out + (static_cast<size_t>(b) * T + q) * a.d + h * DH + half * 32;
+    uint32_t o[32];
+    tmem_ld_x32(tO, o);
+    tmem_wait_ld();
+    if (q < T) {
+      uint4* o4 = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-          o4[i] = w;
-        }
+      for (int i = 0; i < 4; ++i) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+        w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+        w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+        w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+        o4[i] = w;
       }
     }
   }
@@ -339,40 +353,23 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
-// "attn_p_tmem": 0 = P through shared memory (validated default), 1 = P through tensor memory (experimental until
-// measured).  vnb_set_option, else environment VNB_ATTN_P_TMEM.
-static int g_attn_p_tmem = -1;
-void set_attn_p_tmem(int v) { g_attn_p_tmem = v ? 1 : 0; }
-int get_attn_p_tmem() {
-  if (g_attn_p_tmem < 0) {
-    const char* e = getenv("VNB_ATTN_P_TMEM");
-    g_attn_p_tmem = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return g_attn_p_tmem;
-}
+}  // namespace att
 
 cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st) {
-  if (get_attn_v2()) return launch_attention2(p, st);
   static PerDeviceOnce once;
   int dev;
   if (once.need(&dev)) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ATT_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(attention_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(att::attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, att::SMEM);
     if (e != cudaSuccess) return e;
     once.mark(dev);
   }
-  if (p.sat > ATT_MAX_SAT || p.sat < 1) return cudaErrorInvalidValue;
-  AttnArgs a;
+  if (p.sat > att::MAX_SAT || p.sat < 1) return cudaErrorInvalidValue;
+  att::Args a;
   a.out = reinterpret_cast<__nv_bfloat16*>(p.out);
   a.rel = p.rel;
-  a.sat = p.sat; a.B = p.B; a.T = p.T; a.H = p.H; a.d = p.H * DH;
-  dim3 grid((p.T + AQ - 1) / AQ, p.H, p.B);
-  if (get_attn_p_tmem())
-    attention_tcgen05_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(p.tmQ, p.tmK, p.tmVT, a);
-  else
-    attention_tcgen05_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(p.tmQ, p.tmK, p.tmVT, a);
+  a.sat = p.sat; a.B = p.B; a.T = p.T; a.H = p.H; a.d = p.H * att::DH;
+  dim3 grid((p.T + att::AQ - 1) / att::AQ, p.H, p.B);
+  att::attention_tcgen05_kernel<<<grid, att::THREADS, att::SMEM, st>>>(p.tmQ, p.tmK, p.tmVT, a);
   return cudaGetLastError();
 }
 

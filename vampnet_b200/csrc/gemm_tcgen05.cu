@@ -21,9 +21,6 @@
 #include "common.cuh"
 #include "kernels.h"
 
-#ifndef VNB_RESID_TMA_DEFAULT
-#define VNB_RESID_TMA_DEFAULT 0
-#endif
 #ifndef VNB_GEMM_PAIR_DEFAULT
 #define VNB_GEMM_PAIR_DEFAULT true
 #endif
@@ -37,12 +34,6 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_STG_BYTES = 8 * 32 * 36 * 4 - 3072;  // epilogue staging: 4 warps x 32x36 floats, or 8 warps x 32x33 (RESID)
 constexpr int RING_BYTES = STAGES * STAGE_BYTES;  // 192 KiB: 4 x {A 16K, W 32K}, or (CTA pair) 6 x {A 16K, W-half 16K}
 constexpr int GEMM_SMEM = RING_BYTES + GEMM_STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-// TMA residual epilogue (CTA pair only): 3-stage ring + per epilogue warp {3 x 4 KiB fp32 tiles, 2 x 2 KiB bf16 tiles}
-constexpr int TE_STAGES = 3;
-constexpr int TE_RING = TE_STAGES * (A_BYTES + B_BYTES / 2);
-constexpr int TE_WARP_BYTES = 3 * 4096 + 2 * 2048;
-constexpr int TE_SMEM = TE_RING + 8 * TE_WARP_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
-static_assert(TE_SMEM <= 232448, "shared memory budget");
 // The residual epilogue is bound by memory-level parallelism (residual rows must be fetched before they can be
 // updated): it gets 8 epilogue warps, two per TMEM lane quadrant, splitting the 32-column chunks even / odd.
 template <int EPI> constexpr int gemm_epi_warps() { return EPI == VNB_EPI_RESID ? 8 : 4; }
@@ -94,8 +85,8 @@ __device__ __forceinline__ void stage_rows33(float* stg, int lane, const float (
   __syncwarp();
 }
 
-// Sum of squares of four consecutive outputs, in a fixed operation order: both residual epilogues (register-staged and
-// TMA) use it, so the fused RMSNorm statistics do not depend on which one ran.
+// Sum of squares of four consecutive outputs, in a fixed operation order (the fused RMSNorm statistics are
+// deterministic).
 __device__ __forceinline__ float sumsq4(float x, float y, float z, float w) {
   return __fmaf_rn(w, w, __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
 }
@@ -176,24 +167,23 @@ __device__ __forceinline__ void drain_bf16(__nv_bfloat16* out, int pitch, int M,
 // shared memory and read by the tensor core per flop (the kernels run power-capped: bytes moved per flop is what
 // sets the clock), and the smaller stage buys a 6-deep ring in the same 192 KiB.
 //
-// TMAEPI = true (EPI_RESID on CTA pairs): the residual update x += A.W^T is bound by how many bytes of x an SM keeps in
-// flight (ncu: tensor pipe 44 %, DRAM 44 %, neither saturated, with register-staged prefetch).  Here every epilogue warp
-// runs a private TMA pipeline over its 32 x 32 fp32 tiles of x: tile in (two loads in flight, no registers held),
-// add the accumulator rows in place in shared memory, tile out, plus the bf16 copy as a second TMA store.  The 128B /
-// 64B swizzles make the lane-per-row accesses bank-conflict free.  Shared memory is paid for with a 3-stage ring.
-// CTAARRIVE (option "pair_arrive_cta", CTA pairs only): the accumulator-drained arrival uses the .cta-scope release.
-template <int EPI, bool PAIR, bool TMAEPI, bool CTAARRIVE>
+// The accumulator-drained arrival of the epilogue warps on the MMA-issuing CTA's barrier uses the default (.cta-scope)
+// release: the waiter only depends on TMEM reads that have already completed (tcgen05.wait::ld), so the
+// MEMBAR.ALL.GPU that .release.cluster compiles to (11 % of the residual epilogue's stall samples in round 1) is not
+// needed.  Measured bit-identical and 3 % faster on the residual GEMMs (profiles/bench_r2_variants.txt).
+//
+// A residual epilogue that moved its x tiles by TMA (tile in, add in shared memory, tile out) was measured in round 1:
+// bit-identical but 8-30 % slower than the register-staged prefetch below (profiles/bench_r1_resid_tma*.json); removed.
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                     const GemmArgs g) {
-  static_assert(!TMAEPI || (PAIR && EPI == VNB_EPI_RESID), "TMA epilogue: residual GEMM on CTA pairs only");
-  constexpr int NSTAGE = TMAEPI ? TE_STAGES : (PAIR ? 6 : STAGES);
+  constexpr int NSTAGE = PAIR ? 6 : STAGES;
   constexpr int W_BYTES = PAIR ? B_BYTES / 2 : B_BYTES;
   constexpr int STAGE_SZ = A_BYTES + W_BYTES;
   constexpr int RING = NSTAGE * STAGE_SZ;
-  static_assert(TMAEPI ? RING == TE_RING : RING == RING_BYTES, "ring size");
-  constexpr int EPI_REGION = TMAEPI ? 8 * TE_WARP_BYTES : GEMM_STG_BYTES;
+  static_assert(RING == RING_BYTES, "ring size");
+  constexpr int EPI_REGION = GEMM_STG_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms are 1024 B: align the tile ring to 1024.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -202,8 +192,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + NSTAGE;
   uint64_t* tfull_bar = empty_bar + NSTAGE;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
-  uint64_t* lbar_all = tempty_bar + 2;       // TMAEPI: [8 warps][3] residual tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar_all + (TMAEPI ? 24 : 0));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -229,11 +218,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tfull_bar[a], 1);
       // one elected lane of each epilogue warp (of both CTAs in a pair: rank 0's barrier gates the next MMA)
       mbar_init(&tempty_bar[a], gemm_epi_warps<EPI>() * (PAIR ? 2 : 1));
-    }
-    if constexpr (TMAEPI) {
-      for (int i = 0; i < 24; ++i) mbar_init(&lbar_all[i], 1);
-      tma_prefetch_desc(&tmR);
-      tma_prefetch_desc(&tmO);
     }
     mbar_fence_init();
   }
@@ -322,120 +306,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc]);
         else umma_commit(&tfull_bar[acc]);
       }
-    }
-  } else if (warp >= 4 && TMAEPI) {
-    // ===================== epilogue, residual tiles through TMA =====================
-    if constexpr (TMAEPI) {
-      const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-      const int ew = warp - 4;    // 0..7
-      const int half = ew >> 2;   // this warp takes the 32-column chunks with (c & 1) == half
-      uint8_t* ebase = smem + RING + ew * TE_WARP_BYTES;  // 3 fp32 tiles (1024-aligned), then 2 bf16 tiles
-      uint64_t* lbar = lbar_all + ew * 3;
-      const bool fused_out = g.out_bf16 != nullptr;
-      const int my_tiles = worker < num_tiles ? (num_tiles - worker + num_workers - 1) / num_workers : 0;
-      const int total_jobs = my_tiles * 4;  // job j: tile j/4 of this CTA, chunk half + 2*(j%4)
-      auto coords = [&](int j, int& row0, int& col0, int& n0) {
-        const int tile = worker + (j >> 2) * num_workers;
-        row0 = (tile / num_n) * TM + static_cast<int>(rank) * BM + quad * 32;
-        n0 = (tile % num_n) * BN;
-        col0 = n0 + (half + 2 * (j & 3)) * 32;
-      };
-      auto issue_load = [&](int j) {  // lane 0
-        if (j < total_jobs) {
-          int row0, col0, n0;
-          coords(j, row0, col0, n0);
-          const int b = j % 3;
-          mbar_expect_tx(&lbar[b], 4096);
-          tma_load_2d(ebase + b * 4096, &tmR, &lbar[b], col0, row0);  // rows >= M arrive as zeros
-        }
-      };
-      if (lane == 0) {
-        issue_load(0);
-        issue_load(1);
-      }
-      // swizzles as TMA lays the tiles out: fp32 rows are 128 B (16-byte slot i of row r at slot i ^ (r & 7)),
-      // bf16 rows are 64 B (slot q of row r at slot q ^ ((r >> 1) & 3)); this lane owns row `lane` of the tile
-      const uint32_t sw128 = lane & 7, sw64 = (lane >> 1) & 3;
-      float ssacc[8];
-      float rs = 1.0f;
-#pragma unroll 1
-      for (int j = 0; j < total_jobs; ++j) {
-        const int it = j >> 2;
-        const int acc = it & 1;
-        int row0, col0, n0;
-        coords(j, row0, col0, n0);
-        const int row = row0 + lane;
-        if ((j & 3) == 0) {
-          rs = 1.0f;
-          if (g.ss_in != nullptr && row < g.M) {
-            float t = 0.f;
-            for (int p = 0; p < g.ss_parts; ++p) t += __ldg(g.ss_in + static_cast<size_t>(p) * g.M + row);
-            rs = rsqrtf(t * g.inv_d + g.eps);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) ssacc[i] = 0.f;
-          mbar_wait(&tfull_bar[acc], (it >> 1) & 1, 400 + acc);
-          tc_fence_after();
-        }
-        const int c = half + 2 * (j & 3);
-        uint32_t v[32];
-        tmem_ld_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32, v);
-        const int b = j % 3;
-        mbar_wait(&lbar[b], (j / 3) & 1, 500 + b);
-        tmem_wait_ld();
-        const uint32_t fb = smem_u32(ebase + b * 4096) + lane * 128;
-        const uint32_t ob = smem_u32(ebase + 3 * 4096 + (j & 1) * 2048) + lane * 64;
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t addr = fb + ((static_cast<uint32_t>(i) ^ sw128) << 4);
-          const float4 r = lds_f4(addr);
-          float4 a;
-          a.x = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * i + 0]), rs), r.x);
-          a.y = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * i + 1]), rs), r.y);
-          a.z = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * i + 2]), rs), r.z);
-          a.w = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * i + 3]), rs), r.w);
-          sts_f4(addr, a);
-          ssacc[i] = __fadd_rn(ssacc[i], sumsq4(a.x, a.y, a.z, a.w));
-          pk[2 * i] = pack_bf16x2(a.x, a.y);
-          pk[2 * i + 1] = pack_bf16x2(a.z, a.w);
-        }
-        if (fused_out) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            sts_v4(ob + ((static_cast<uint32_t>(q) ^ sw64) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-        fence_proxy_async_smem();  // the TMA stores below read what the lanes just wrote
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmR, ebase + b * 4096, col0, row0);  // rows >= M are clipped
-          if (fused_out) tma_store_2d(&tmO, ebase + 3 * 4096 + (j & 1) * 2048, col0, row0);
-          bulk_commit();
-          // all but this job's stores have finished reading shared memory: the fp32 tile of job j-1 (where the load
-          // of job j+2 lands) and the bf16 tile of job j-1 (rewritten by job j+1) are free
-          bulk_wait_read<1>();
-          issue_load(j + 2);
-        }
-        __syncwarp();
-        if ((j & 3) == 3) {
-          if (fused_out) {
-            // same pairwise order as the shuffle tree of the register-staged epilogue
-            const float t01 = __fadd_rn(ssacc[0], ssacc[1]), t23 = __fadd_rn(ssacc[2], ssacc[3]);
-            const float t45 = __fadd_rn(ssacc[4], ssacc[5]), t67 = __fadd_rn(ssacc[6], ssacc[7]);
-            const float tot = __fadd_rn(__fadd_rn(t01, t23), __fadd_rn(t45, t67));
-            const int part = (n0 / BN) * 2 + half;
-            if (row < g.M) g.ss_out[static_cast<size_t>(part) * g.M + row] = tot;
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            const uint32_t bar0 = mapa_u32(smem_u32(&tempty_bar[acc]), 0);
-            if constexpr (CTAARRIVE) mbar_arrive_remote_cta(bar0);
-            else mbar_arrive_cluster(bar0);
-          }
-        }
-      }
-      if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last stores' reads
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -568,10 +438,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) {
         if constexpr (PAIR) {
           const uint32_t bar0 = mapa_u32(smem_u32(&tempty_bar[acc]), 0);
-          // .release.cluster costs a MEMBAR.ALL.GPU per tile and warp (ncu: 11 % of the residual epilogue's samples);
-          // the .cta-scope form is sufficient here (see common.cuh) and becomes the default once measured
-          if constexpr (CTAARRIVE) mbar_arrive_remote_cta(bar0);
-          else mbar_arrive_cluster(bar0);
+          mbar_arrive_remote_cta(bar0);  // .cta-scope release, see the note above the kernel
         }
         else mbar_arrive(&tempty_bar[acc]);
       }
@@ -604,31 +471,6 @@ static bool gemm_pair_enabled() {
 }
 int get_gemm_pair() { return gemm_pair_enabled() ? 1 : 0; }
 
-// "pair_arrive_cta": selects the CTAARRIVE instantiations (see the kernel template).  Environment VNB_PAIR_ARRIVE_CTA, default 0 (the validated form).
-static int g_pair_arrive_cta = -1;
-void set_pair_arrive_cta(int v) { g_pair_arrive_cta = v ? 1 : 0; }
-int get_pair_arrive_cta() {
-  if (g_pair_arrive_cta < 0) {
-    const char* e = getenv("VNB_PAIR_ARRIVE_CTA");
-    g_pair_arrive_cta = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return g_pair_arrive_cta;
-}
-
-// Residual GEMMs (attention output, FFN down) with the TMA epilogue: vnb_set_option("resid_tma", v), else the
-// environment variable VNB_RESID_TMA, else the compiled default.  0 = register-staged epilogue, 1 = TMA epilogue when
-// K <= 1280 (the epilogue-bound attention-output projection), 2 = always.  Needs the CTA-pair kernel.
-static int g_resid_tma = -1;
-void set_resid_tma(int v) { g_resid_tma = v < 0 ? 0 : (v > 2 ? 2 : v); }
-int get_resid_tma() {
-  if (g_resid_tma < 0) {
-    const char* e = getenv("VNB_RESID_TMA");
-    g_resid_tma = e != nullptr ? (e[0] - '0') : VNB_RESID_TMA_DEFAULT;
-    if (g_resid_tma < 0 || g_resid_tma > 2) g_resid_tma = 0;
-  }
-  return g_resid_tma;
-}
-
 // Once per device and epilogue: opt in to the large dynamic shared memory for both tile variants and ask how many CTA
 // pairs can be co-resident (one CTA per SM, both SMs of a TPC).  Called eagerly by prepare_gemm() (model creation), so
 // that none of this runs inside a stream capture.
@@ -638,22 +480,10 @@ static cudaError_t init_epi() {
   static PerDeviceOnce once;
   int dev;
   if (!once.need(&dev)) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       GEMM_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           GEMM_SMEM);
-  if (e != cudaSuccess) return e;
-  if constexpr (EPI == VNB_EPI_RESID) {
-    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<VNB_EPI_RESID, true, true, false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<VNB_EPI_RESID, true, true, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM);
-    if (e != cudaSuccess) return e;
-  }
   cudaLaunchConfig_t q = {};
   q.gridDim = dim3(2 * device_sm_count());
   q.blockDim = dim3(gemm_threads<EPI>());
@@ -663,7 +493,7 @@ static cudaError_t init_epi() {
   qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
   q.attrs = qa; q.numAttrs = 1;
   int n = 0;
-  e = cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<EPI, true, false, false>, &q);
+  e = cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<EPI, true>, &q);
   if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = device_sm_count() / 2; }
   if (dev >= 0 && dev < 64) g_max_clusters[EPI][dev] = n;
   once.mark(dev);
@@ -705,25 +535,11 @@ static cudaError_t launch_epi(const GemmPlan& p, const GemmArgs& g, cudaStream_t
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if constexpr (EPI == VNB_EPI_RESID) {
-      const int mode = get_resid_tma();
-      const bool maps_ok = p.has_tmR && (p.out_bf16 == nullptr || p.has_tmO);
-      if (maps_ok && (mode == 2 || (mode == 1 && g.K <= 1280))) {
-        cfg.dynamicSmemBytes = TE_SMEM;
-        if (get_pair_arrive_cta())
-          return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<VNB_EPI_RESID, true, true, true>, p.tmA, p.tmBh, p.tmR,
-                                    p.tmO, g);
-        return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<VNB_EPI_RESID, true, true, false>, p.tmA, p.tmBh, p.tmR,
-                                  p.tmO, g);
-      }
-    }
-    if (get_pair_arrive_cta())
-      return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI, true, false, true>, p.tmA, p.tmBh, p.tmR, p.tmO, g);
-    return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI, true, false, false>, p.tmA, p.tmBh, p.tmR, p.tmO, g);
+    return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI, true>, p.tmA, p.tmBh, g);
   }
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tcgen05_kernel<EPI, false, false, false><<<grid, gemm_threads<EPI>(), GEMM_SMEM, st>>>(p.tmA, p.tmB, p.tmR, p.tmO, g);
+  gemm_tcgen05_kernel<EPI, false><<<grid, gemm_threads<EPI>(), GEMM_SMEM, st>>>(p.tmA, p.tmB, g);
   return cudaGetLastError();
 }
 

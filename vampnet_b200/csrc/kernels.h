@@ -45,9 +45,6 @@ namespace vnb {
 struct GemmPlan {
   CUtensorMap tmA, tmB;
   CUtensorMap tmBh;  // W with a 128-row box: the half tile each CTA of a pair stages (gemm_tcgen05.cu, PAIR)
-  CUtensorMap tmR;   // EPI_RESID: fp32 residual stream, 32 x 32 box (TMA epilogue: tile in, updated tile out)
-  CUtensorMap tmO;   // EPI_RESID + fused out: bf16 copy, 32 x 32 box
-  bool has_tmR = false, has_tmO = false;
   int M = 0, N = 0, K = 0, epi = 0;
   void* out = nullptr;
   void* out2 = nullptr;
@@ -64,18 +61,10 @@ struct GemmPlan {
 bool make_gemm_plan(GemmPlan* p, int epi, const void* A, const void* W, int M, int N, int K, void* out, void* out2,
                     const float* bias, int T, int Tpad, int d2);
 bool gemm_plan_set_fused_out(GemmPlan* p, void* out_bf16, float* ss_out);
-bool make_tmap_2d_ex(CUtensorMap* tm, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                     uint32_t box_cols, int swizzle_bytes);
 cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t st);
 cudaError_t prepare_gemm();  // per-device kernel attributes; call outside stream capture
 void set_gemm_pair(int on);  // 1: CTA-pair (cta_group::2) GEMM tiles, 0: single-CTA tiles
 int get_gemm_pair();
-void set_pair_arrive_cta(int v);  // CTA pair: accumulator-drained arrival without the cluster-scope fence
-int get_pair_arrive_cta();
-void set_attn_p_tmem(int v);  // attention: probabilities through tensor memory instead of shared memory
-int get_attn_p_tmem();
-void set_resid_tma(int v);  // residual GEMM epilogue through TMA: 0 off, 1 when K <= 1280, 2 always
-int get_resid_tma();
 int get_gemm_max_clusters();  // co-resident CTA pairs of the pair kernel on the current device
 cudaError_t launch_gemm_ref(const void* A, const void* W, int M, int N, int K, float* out, cudaStream_t st);
 
@@ -84,7 +73,6 @@ struct AttnPlan {
   CUtensorMap tmQ;   // (B, T, 2d)  box (1, 128 rows, 64 cols)
   CUtensorMap tmK;   // (B, T, 2d)  box (1, 64 rows, 64 cols)
   CUtensorMap tmVT;  // (B, d, Tpad) box (1, 64 rows, 64 cols)
-  CUtensorMap tmK128;  // (B, T, 2d)  box (1, 128 rows, 64 cols): 128-key blocks of the second attention design
   void* out = nullptr;         // (B, T, d) bf16
   const float* rel = nullptr;  // (2*sat+1, H)
   int sat = 0, B = 0, T = 0, Tpad = 0, H = 0;
@@ -92,9 +80,6 @@ struct AttnPlan {
 bool make_attn_plan(AttnPlan* p, const void* qk, const void* vT, void* out, const float* rel, int sat, int B, int T,
                     int Tpad, int H);
 cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st);
-cudaError_t launch_attention2(const AttnPlan& p, cudaStream_t st);  // attention2_tcgen05.cu (option "attn_v2")
-void set_attn_v2(int v);
-int get_attn_v2();
 
 // ---- elementwise / gather ----
 cudaError_t launch_rmsnorm(const float* x, const float* w, void* y_bf16, int M, int d, float eps, cudaStream_t st);

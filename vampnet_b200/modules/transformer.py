@@ -243,6 +243,12 @@ class VampNet(nn.Module):
         """Cold model: plain nn.Module load.  Live model (a device handle exists): hot swap — parameters are
         overwritten in place and the packed device buffers the handle, its tensor maps and its captured generate
         graphs point at are rewritten in place, so no workspace, tensor map or graph is rebuilt."""
+        flash = [k for k in state_dict if ".self_attn.Wqkv." in k or ".self_attn.out_proj." in k]
+        if flash:
+            raise RuntimeError(
+                f"state_dict holds FlashMHA tensors ({flash[0]} ...): a flash_attn=True checkpoint has no relative "
+                "position bias and different projection names; this implementation covers the flash_attn=False "
+                "architecture the released VampNet checkpoints use (conf/vampnet.yml:33)")
         live = self._handle is not None and getattr(self, "_packed_codec", None) is not None
         if not live:
             self._invalidate()
@@ -306,7 +312,12 @@ class VampNet(nn.Module):
         import inspect
         ok = set(inspect.signature(cls.__init__).parameters)
         model = cls(**{k: v for k, v in ctor.items() if k in ok})
-        model.load_state_dict(blob["state_dict"], strict=strict)
+        res = model.load_state_dict(blob["state_dict"], strict=strict)
+        # strict=False (how the reference loads, interface.py:34) tolerates absent LoRA adapters, nothing else: a
+        # checkpoint of another architecture would otherwise leave projections at their random initialisation
+        missing = [k for k in getattr(res, "missing_keys", []) if ".lora_" not in k]
+        if missing:
+            raise RuntimeError(f"checkpoint {location} lacks {len(missing)} tensors of this architecture, e.g. {missing[:3]}")
         return model
 
     # ------------------------------------------------------------------ weight packing
@@ -396,8 +407,6 @@ class VampNet(nn.Module):
         (reference transformer.py:617-639).  Returned as a permuted view of the kernel's (B, S, V) buffer."""
         if ctrls is not None or ctrl_masks is not None:
             raise NotImplementedError("controls are outside the hot path (SURVEY.md §8)")
-        if return_activations:
-            raise NotImplementedError("return_activations is only used by offline tooling (SURVEY.md §2 row 19)")
         if self._handle is None:
             self._codec_stub = self._NoCodec(self.n_codebooks, self.vocab_size, self.latent_dim, self.device)
             self._ensure_handle(self._codec_stub)
@@ -407,6 +416,11 @@ class VampNet(nn.Module):
         S = T * self.n_predict_codebooks
         logits = torch.empty(B, S, self.vocab_size, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
+            if return_activations:  # the residual stream after every layer (reference :443-461, :626-637)
+                acts = torch.empty(self.n_layers, B, T, self.embedding_dim, device=self.device, dtype=torch.float32)
+                _lib.check(_lib.lib().vnb_forward_latents_acts(self._handle, _lib.ptr(x), B, T, _lib.ptr(logits),
+                                                               _lib.ptr(acts), _lib.stream_ptr(self.device)))
+                return logits.permute(0, 2, 1), acts
             _lib.check(_lib.lib().vnb_forward_latents(self._handle, _lib.ptr(x), B, T, _lib.ptr(logits),
                                                       _lib.stream_ptr(self.device)))
         return logits.permute(0, 2, 1)
@@ -485,8 +499,8 @@ class VampNet(nn.Module):
         if mask is not None:
             if mask.ndim == 2:
                 mask = mask[:, None, :].repeat(1, C_, 1)
-            m32 = (mask.to(dev) != 0).to(torch.int32).contiguous()
-            assert m32.shape == z.shape
+            # the reference applies the mask with z.masked_fill(mask.bool(), ...) (:762): broadcastable masks are legal
+            m32 = (mask.to(dev) != 0).expand_as(z).to(torch.int32).contiguous()
         # Philox key: from the seed when given, else from torch's (possibly user-seeded) global generator
         if seed is not None:
             k = int(seed) & 0xFFFFFFFFFFFFFFFF
