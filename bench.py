@@ -1,16 +1,20 @@
 #!/usr/bin/env python
 """bench.py — VampNet masked-token generation hot path on B200 (contract in the task statement).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (oracle port of the reference)
-    torchrun ... bench.py --gpus N ...                        # N>1: one rank per GPU, weak scaling
+    python bench.py --gpus N --steps K --warmup W [--config {1,2,3,4}]     # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W         # CPU arm (oracle port of the reference)
+    torchrun ... bench.py --gpus N ...                                     # N>1: one rank per GPU, weak scaling
 
-Workload (BASELINE.json configs[2], the configuration the metric "coarse+c2f" is quoted on; fits one GPU):
-one "step" = coarse VampNet.generate (4 codebooks, d=1280, 20 layers, 12 sampling steps) followed by
-coarse-to-fine VampNet.generate (14 codebooks, 4 conditioning, 16 layers, 24 sampling steps, unchunked) on
-B=32 clips of T=768 frames per GPU, default sampling parameters (temperature 1, mask_temperature 10.5),
-random-init weights, synthetic random codes, periodic prompt every 7th frame.  value = codec tokens/s =
-N*B*T*14 / time.  Real-time factor = N*B*T*768/44100 / time.
+--config selects BASELINE.json configs[k] (default 2, the configuration the metric "coarse+c2f" is quoted on):
+  1  coarse generate: 12 sampling steps, T=768, B=8 per GPU
+  2  coarse -> c2f full vamp: 12 + 24 steps, codebooks 4 -> 14, T=768, B=32 per GPU, unchunked
+  3  DAC encode -> vamp -> DAC decode end to end through Interface, 10 s 44.1 kHz clips (T=575), 32 clips per GPU
+     (256 over 8 GPUs), coarse 12 + c2f 24 steps; `value` has the audio resident in HBM, `e2e` host audio in / out
+  4  long-context coarse: T=3072 (~40 s), 24 steps, B=8 per GPU (64 over 8 GPUs)
+One "step" = one pass of that workload over one batch of synthetic input (random-init weights, random codes /
+synthetic audio, periodic prompt every 7th frame, default sampling parameters: temperature 1, mask_temperature 10.5).
+value = codec tokens/s = N*B*T*C_out / time (C_out = 4 for the coarse-only configs, 14 otherwise); real-time factor
+= N*B*T*768/44100 / time.
 """
 from __future__ import annotations
 
@@ -30,13 +34,30 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-T_FRAMES = 768
-BATCH = 32
 COARSE = dict(n_heads=20, n_layers=20, n_codebooks=4, n_conditioning_codebooks=0, embedding_dim=1280)
 C2F = dict(n_heads=20, n_layers=16, n_codebooks=14, n_conditioning_codebooks=4, embedding_dim=1280)
-COARSE_STEPS, C2F_STEPS = 12, 24
 HOP, SR = 768, 44100
-METRIC = "codec tokens/sec (coarse 12 steps + c2f 24 steps generate, T=768, 44.1 kHz)"
+CONFIGS = {
+    1: dict(B=8, T=768, stages=(("coarse", 12),), c_out=4, codec=False,
+            metric="codec tokens/sec (coarse generate 12 steps, T=768, 44.1 kHz)",
+            workload="BASELINE.json configs[1]: coarse generate 12 steps (4 codebooks, 20 layers, d=1280), default sampling"),
+    2: dict(B=32, T=768, stages=(("coarse", 12), ("c2f", 24)), c_out=14, codec=False,
+            metric="codec tokens/sec (coarse 12 steps + c2f 24 steps generate, T=768, 44.1 kHz)",
+            workload="BASELINE.json configs[2]: coarse generate 12 steps (4 codebooks, 20 layers) -> c2f "
+                     "generate 24 steps (14 codebooks, 16 layers), unchunked, d=1280, default sampling"),
+    3: dict(B=32, T=575, stages=(("coarse", 12), ("c2f", 24)), c_out=14, codec=True,
+            metric="codec tokens/sec (DAC encode -> coarse 12 + c2f 24 steps -> DAC decode, 10 s clips, 44.1 kHz)",
+            workload="BASELINE.json configs[3]: Interface.encode -> coarse_vamp (12 steps) -> coarse_to_fine (24 steps, "
+                     "unchunked) -> Interface.decode on 10 s 44.1 kHz clips (441 000 samples -> 575 frames); codec = "
+                     "DAC-family stand-in (lac is not available), tensor-core path"),
+    4: dict(B=8, T=3072, stages=(("coarse", 24),), c_out=4, codec=False,
+            metric="codec tokens/sec (long-context coarse generate 24 steps, T=3072, 44.1 kHz)",
+            workload="BASELINE.json configs[4]: coarse generate 24 steps, T=3072 (~40 s), d=1280, 20 layers"),
+}
+MODEL_CFG = {"coarse": COARSE, "c2f": C2F}
+# codec algorithmic work per 10 s clip (stand-in configuration): fp32 layer-by-layer bytes, flops
+CODEC_BYTES = {"encode": 8.3e9, "decode": 12.4e9}
+CODEC_FLOPS = {"encode": 0.61e12, "decode": 1.37e12}
 
 
 def fwd_flops(cfg, T):
@@ -160,53 +181,76 @@ def host_threads():
     return n
 
 
-def cpu_sample(threads):
+def cpu_sample(threads, cfg):
     """Bounded sample of the same workload on the host cores through the oracle port of the reference
-    (oracle/vampnet_oracle.py, fp32 like the reference's CPU path): one coarse and one c2f sampling iteration
-    (forward + sample + remask) at B=1, T=768, extrapolated to 12 + 24 iterations per clip."""
+    (oracle/vampnet_oracle.py, fp32 like the reference's CPU path): ONE sampling iteration (forward + sample + remask)
+    of every stage at B=1 and the config's T, extrapolated to the config's iteration counts per clip; for the
+    end-to-end config also one encode + decode of one clip through the codec oracle.  The port leaves out work the
+    reference does and discards (typical_filter, transformer.py:989-993: ~30 % of its sampling time),
+    so the unmodified reference is somewhat SLOWER than this number."""
     from oracle import vampnet_oracle as vo
     torch.set_num_threads(threads)
     res = {}
     g = torch.Generator().manual_seed(0)
-    for tag, cfgd in (("coarse", COARSE), ("c2f", C2F)):
-        cfg = vo.OracleConfig(**cfgd)
-        sd = vo.make_state_dict(cfg, seed=0)
-        orc = vo.OracleVampNet(cfg, sd, "fp32")
-        cb = vo.make_codebooks(cfg.n_codebooks, seed=1)
-        z = torch.randint(0, 1024, (1, cfg.n_codebooks, T_FRAMES), generator=g)
+    T = cfg["T"]
+    for tag, steps in cfg["stages"]:
+        ocfg = vo.OracleConfig(**MODEL_CFG[tag])
+        sd = vo.make_state_dict(ocfg, seed=0)
+        orc = vo.OracleVampNet(ocfg, sd, "fp32")
+        cb = vo.make_codebooks(ocfg.n_codebooks, seed=1)
+        z = torch.randint(0, 1024, (1, ocfg.n_codebooks, T), generator=g)
         mask = torch.ones_like(z)
         mask[:, :, ::7] = 0
-        mask[:, :cfg.n_conditioning_codebooks] = 0
+        mask[:, :ocfg.n_conditioning_codebooks] = 0
         t0 = time.perf_counter()
         orc.generate(cb, z, mask, _sampling_steps=1, seed=0, rng="torch")
         res[tag] = time.perf_counter() - t0
         del orc, sd
-    clip_s = COARSE_STEPS * res["coarse"] + C2F_STEPS * res["c2f"]
-    return T_FRAMES * 14 / clip_s, res
+    clip_s = sum(steps * res[tag] for tag, steps in cfg["stages"])
+    if cfg["codec"]:
+        from oracle import dac_oracle as do
+        ccfg = do.CodecConfig()
+        w = do.make_codec_weights(ccfg, seed=0)
+        x = 0.3 * torch.randn(1, 1, T * HOP, generator=g)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            enc = do.encode(x, w, ccfg)
+            do.decode(enc["z"], w, ccfg)
+        res["codec"] = time.perf_counter() - t0
+        clip_s += res["codec"]
+    return T * cfg["c_out"] / clip_s, res
+
+
+def cpu_sample_text(cfg, parts, threads):
+    it = " + ".join(f"1 {tag} sampling iteration ({parts[tag]:.2f}s)" for tag, _ in cfg["stages"])
+    ex = "+".join(str(n) for _, n in cfg["stages"])
+    codec = f" + one codec-oracle encode/decode of a 10 s clip ({parts['codec']:.1f}s)" if cfg["codec"] else ""
+    return (f"{it} at B=1,T={cfg['T']} via the oracle port (fp32, {threads} threads), extrapolated to {ex} iterations "
+            f"per clip{codec}; the port omits the reference's discarded typical_filter work, so the unmodified "
+            f"reference is slower than this")
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     threads = host_threads()
     vals = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        v, parts = cpu_sample(threads)
+        v, parts = cpu_sample(threads, cfg)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             vals.append((v, dt))
     v = statistics.mean(x[0] for x in vals)
-    sample = ("per step: 1 coarse + 1 c2f sampling iteration at B=1,T=768 through the oracle port (fp32, "
-              f"{threads} threads), extrapolated to 12+24 iterations per clip")
     line = {
-        "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+        "metric": cfg["metric"], "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(x[1] for x in vals), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "rtf": v / 14 * HOP / SR,
-        "config": {"workload": "BASELINE.json configs[2] (coarse 12 + c2f 24 steps, T=768), bounded CPU sample at B=1",
-                   "seq_len": T_FRAMES, "global_batch": 1},
-        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+        "rtf": v / cfg["c_out"] * HOP / SR,
+        "config": {"workload": cfg["workload"] + "; bounded CPU sample at B=1", "seq_len": cfg["T"], "global_batch": 1},
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
+                         "sample": "per step: " + cpu_sample_text(cfg, parts, threads)},
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -249,6 +293,46 @@ def emit(line: dict):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
+def secondary_rooflines(cfg, B, fam_ms, fam_n, fl, peaks, codec_ms):
+    """The kernels the north-star classifies by HBM bandwidth, and attention by tensor throughput, next to the headline
+    GEMM family: achieved = ALGORITHMIC bytes (or flops) of the launches of one profiled step / their CUDA-event time."""
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    out = []
+    T = cfg["T"]
+    logit_bytes = emb_bytes = 0.0
+    for tag, steps in cfg["stages"]:
+        m = MODEL_CFG[tag]
+        Cn, Cp, d = m["n_codebooks"], m["n_codebooks"] - m["n_conditioning_codebooks"], m["embedding_dim"]
+        logit_bytes += steps * B * T * Cp * 1024 * 4.0                        # fp32 logits read once per iteration
+        emb_bytes += steps * B * T * (Cn * (4 + 32) + d * (4 + 2) + 8)        # codes + table rows in, x fp32 + bf16 copy out
+    if fam_ms.get("sample_remask"):
+        a = logit_bytes / (fam_ms["sample_remask"] * 1e-3) / 1e9
+        out.append({"kernel": "sample_rows_kernel + remask_kernel", "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s",
+                    "frac": a / hbm, "algorithmic_bytes_per_step": logit_bytes, "ms_per_step": fam_ms["sample_remask"],
+                    "note": "contract figure: every fp32 logit read once (SURVEY.md 8d); positions already known are "
+                            "skipped by the kernel, so the bytes actually moved are fewer"})
+    if fam_ms.get("embed"):
+        a = emb_bytes / (fam_ms["embed"] * 1e-3) / 1e9
+        out.append({"kernel": "embed (codes -> residual stream)", "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s",
+                    "frac": a / hbm, "algorithmic_bytes_per_step": emb_bytes, "ms_per_step": fam_ms["embed"]})
+    if fam_ms.get("attention"):
+        a = fl["attention"] / (fam_ms["attention"] * 1e-3) / 1e12
+        out.append({"kernel": "attention_tcgen05_kernel", "bound": "tensor", "achieved": a, "peak": tf, "unit": "TFLOP/s",
+                    "frac": a / tf, "ms_per_step": fam_ms["attention"],
+                    "note": "at d_head 64 the exponentials (MUFU) cost twice the tensor cycles: MUFU-bound ceiling = 0.5"})
+    for part in ("encode", "decode"):
+        if codec_ms.get(part):
+            t = codec_ms[part] * 1e-3
+            ab, af = B * CODEC_BYTES[part] / t / 1e9, B * CODEC_FLOPS[part] / t / 1e12
+            out.append({"kernel": f"codec {part} (conv_tcgen05_kernel stack + rvq_kernel)", "bound": "hbm",
+                        "achieved": ab, "peak": hbm, "unit": "GB/s", "frac": ab / hbm, "ms_per_step": codec_ms[part],
+                        "tflops": af, "tensor_frac_of_sustained_bf16": af / tf,
+                        "note": "bytes = fp32 layer-by-layer activation traffic of the stand-in architecture (SURVEY.md 8d); "
+                                "split-bf16 issues 3 MMAs per algorithmic one"})
+    return out
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -256,12 +340,14 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="clips per GPU (default = the named config)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[k]")
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU (default = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = CONFIGS[args.config]
 
     if args.impl == "reference":
         run_reference_arm(args, rank)
@@ -281,32 +367,98 @@ def main():
 
     lib = _lib.lib()
     torch.manual_seed(1234)
+    stage_names = [tag for tag, _ in cfg["stages"]]
+    steps_of = dict(cfg["stages"])
     with torch.device(dev):
-        coarse = VampNet(**COARSE)
-        c2f = VampNet(**C2F)
+        models = {tag: VampNet(**MODEL_CFG[tag]) for tag in stage_names}
         cb = torch.randn(14, 1024, 8)
-    broadcast_weights([coarse, c2f], world)
+    to_bcast = list(models.values())
+    iface = None
+    if cfg["codec"]:
+        from vampnet_b200.codec import DAC
+        from vampnet_b200.interface import Interface
+        dac = DAC()
+        iface = Interface.from_models(dac, models["coarse"], models["c2f"], device=dev, coarse_chunk_size_s=10,
+                                      coarse2fine_chunk_size_s=10)   # s2t(10) = 575 frames: one chunk per clip
+        to_bcast.append(dac)
+    broadcast_weights(to_bcast, world)
     if world > 1:
         dist.broadcast(cb, src=0)
-    codec = _Codec(cb)
+    codec = iface.codec if iface is not None else _Codec(cb)
 
-    B, T = args.batch, T_FRAMES
+    B, T = (args.batch or cfg["B"]), cfg["T"]
     g = torch.Generator().manual_seed(100 + rank)  # every rank vamps its own clips
-    z_host = torch.randint(0, 1024, (B, 14, T), generator=g).pin_memory()
-    mask_host = torch.ones(B, 14, T, dtype=torch.int64)
-    mask_host[:, :, ::7] = 0
-    mask_host = mask_host.pin_memory()
-    z_dev = z_host.to(dev)
-    mask_dev = mask_host.to(dev)
-    mask_c2f_dev = mask_dev.clone()
-    mask_c2f_dev[:, :4] = 0  # conditioning codebooks are never masked (interface.py:355-357)
 
-    def step(z, mask, mask_c2f, seed):
-        zc = coarse.generate(codec, start_tokens=z[:, :4].contiguous(), mask=mask[:, :4].contiguous(),
-                             _sampling_steps=COARSE_STEPS, return_signal=False, seed=seed)
+    def generate_stages(z, mask, mask_c2f, seed):
+        zc = models["coarse"].generate(codec, start_tokens=z[:, :4].contiguous(), mask=mask[:, :4].contiguous(),
+                                       _sampling_steps=steps_of["coarse"], return_signal=False, seed=seed)
+        if "c2f" not in models:
+            return zc
         zin = torch.cat([zc, z[:, 4:]], dim=1)
-        return c2f.generate(codec, start_tokens=zin, mask=mask_c2f, _sampling_steps=C2F_STEPS, return_signal=False,
-                            seed=seed + 1)
+        return models["c2f"].generate(codec, start_tokens=zin, mask=mask_c2f, _sampling_steps=steps_of["c2f"],
+                                      return_signal=False, seed=seed + 1)
+
+    codec_ms = {}
+    if not cfg["codec"]:
+        z_host = torch.randint(0, 1024, (B, 14, T), generator=g).pin_memory()
+        mask_host = torch.ones(B, 14, T, dtype=torch.int64)
+        mask_host[:, :, ::7] = 0
+        mask_host = mask_host.pin_memory()
+        z_dev, mask_dev = z_host.to(dev), mask_host.to(dev)
+        mask_c2f_dev = mask_dev.clone()
+        mask_c2f_dev[:, :4] = 0  # conditioning codebooks are never masked (interface.py:355-357)
+
+        def step_dev(seed):
+            return generate_stages(z_dev, mask_dev, mask_c2f_dev, seed)
+
+        def step_e2e(seed):
+            zd = z_host.to(dev, non_blocking=True)
+            md = mask_host.to(dev, non_blocking=True)
+            mc = md.clone()
+            mc[:, :4] = 0
+            return generate_stages(zd, md, mc, seed).cpu()
+
+        h2d = z_host.numel() * 8 + mask_host.numel() * 8
+        api = " -> ".join(f"VampNet.generate({t})" for t in stage_names) + " with pinned host tensors in, host tensor out"
+    else:
+        from vampnet_b200.audio import AudioSignal
+        n = 441000
+        t = torch.arange(n) / SR
+        f0 = 110.0 + 20.0 * torch.arange(B)[:, None] + 7.0 * rank
+        clips_host = (0.3 * torch.sin(2 * torch.pi * f0 * t[None, :]) + 0.05 * torch.randn(B, n, generator=g))[:, None, :]
+        clips_host = clips_host.contiguous().pin_memory()
+        clips_dev = clips_host.to(dev)
+
+        def pipeline(audio_dev, seed, timed=None):
+            """Interface.encode -> build_mask -> coarse_vamp -> coarse_to_fine -> decode (reference interface.py:220,
+            454, 383, 328, 203); `timed` collects CUDA-event times of the codec halves."""
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed is not None else None
+            if ev:
+                ev[0].record()
+            codes = iface.encode(AudioSignal(audio_dev, SR))                   # (B, 14, 575)
+            if ev:
+                ev[1].record()
+            mask = iface.build_mask(codes, None, periodic_prompt=7, upper_codebook_mask=3)
+            zc = iface.coarse_vamp(codes, mask, _sampling_steps=steps_of["coarse"], seed=seed)
+            z = iface.coarse_to_fine(zc, mask=mask, _sampling_steps=steps_of["c2f"], seed=seed + 1)
+            if ev:
+                ev[2].record()
+            out = iface.decode(z)
+            if ev:
+                ev[3].record()
+                torch.cuda.synchronize()
+                timed["encode"], timed["decode"] = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
+            return out.samples
+
+        def step_dev(seed):
+            return pipeline(clips_dev, seed)
+
+        def step_e2e(seed):
+            return pipeline(clips_host.to(dev, non_blocking=True), seed).cpu()
+
+        h2d = clips_host.numel() * 4
+        api = ("Interface.encode -> build_mask -> coarse_vamp -> coarse_to_fine -> Interface.decode with pinned host "
+               "audio in, host audio out")
 
     def barrier():
         if world > 1:
@@ -314,9 +466,12 @@ def main():
         torch.cuda.synchronize()
 
     for i in range(args.warmup):
-        out = step(z_dev, mask_dev, mask_c2f_dev, 10 + 2 * i)
+        out = step_dev(10 + 2 * i)
     torch.cuda.synchronize()
-    assert not (out == 1024).any(), "mask tokens survived generate()"
+    if not cfg["codec"]:
+        assert not (out == 1024).any(), "mask tokens survived generate()"
+    else:
+        assert out.shape == (B, 1, 441600) and bool(torch.isfinite(out).all())
 
     # ---- timed region: inputs resident in HBM, production path (CUDA-graph replay) ----
     clocks = ClockSampler(local_rank)
@@ -327,27 +482,22 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        out = step(z_dev, mask_dev, mask_c2f_dev, 100 + 2 * i)
+        out = step_dev(100 + 2 * i)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.vnb_launch_count() - launches0
     clk = clocks.stop()
 
-    # ---- end to end: host (pinned) inputs, H2D + D2H inside the timed region, public generate() API ----
+    # ---- end to end: host (pinned) inputs, H2D + D2H inside the timed region, public API ----
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        zd = z_host.to(dev, non_blocking=True)
-        md = mask_host.to(dev, non_blocking=True)
-        mc = md.clone()
-        mc[:, :4] = 0
-        res_host = step(zd, md, mc, 200 + 2 * i).cpu()
+        res_host = step_e2e(200 + 2 * i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
-    h2d = z_host.numel() * 8 + mask_host.numel() * 8
-    d2h = res_host.numel() * 8
+    d2h = res_host.numel() * res_host.element_size()
 
     # max over ranks
     tms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
@@ -359,21 +509,24 @@ def main():
     fam_ms = {k: 0.0 for k in _lib.FAMILIES}
     fam_n = {k: 0 for k in _lib.FAMILIES}
     fl = {}
-    for model, cfgd, nsteps in ((coarse, COARSE, COARSE_STEPS), (c2f, C2F, C2F_STEPS)):
-        for k, v in family_flops(cfgd, T, B, nsteps).items():
+    for tag in stage_names:
+        for k, v in family_flops(MODEL_CFG[tag], T, B, steps_of[tag]).items():
             fl[k] = fl.get(k, 0) + v
-    for model in (coarse, c2f):
+    for model in models.values():
         _lib.check(lib.vnb_profile_begin(model._handle))
-    step(z_dev, mask_dev, mask_c2f_dev, 300)
+    if cfg["codec"]:
+        pipeline(clips_dev, 300, timed=codec_ms)
+    else:
+        step_dev(300)
     torch.cuda.synchronize()
-    for model in (coarse, c2f):
+    for model in models.values():
         a = (C.c_float * len(_lib.FAMILIES))()
         n = (C.c_int32 * len(_lib.FAMILIES))()
         _lib.check(lib.vnb_profile_end(model._handle, a, n, len(_lib.FAMILIES)))
         for i, k in enumerate(_lib.FAMILIES):
             fam_ms[k] += a[i]
             fam_n[k] += n[i]
-    prof_total = sum(fam_ms.values())
+    prof_total = sum(fam_ms.values()) + sum(codec_ms.values())
     gemm_keys = [k for k in _lib.FAMILIES if k.startswith("gemm")]
     gemm_ms = sum(fam_ms[k] for k in gemm_keys)
     gemm_fl = sum(fl[k] for k in gemm_keys)
@@ -385,49 +538,51 @@ def main():
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)  # kernel timed inside a long step -> sustained figure
     traffic, traffic_note = ncu_traffic_per_launch()
+    if (B, T) != (32, 768):
+        traffic, traffic_note = None, "the committed ncu capture is of the B=32, T=768 shape"
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {
         "kernel": "gemm_tcgen05_kernel<EPI, PAIR=true> (CTA pairs, tcgen05.mma.cta_group::2, 256x256 tiles; all epilogues: qkv, attn-out+residual, ffn-up+GEGLU, ffn-down+residual, classifier+bias)",
         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
         "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write)", "traffic_source": traffic_note,
-        "algorithmic_bytes_per_launch": gemm_algorithmic_bytes(B, T) ,
+        "algorithmic_bytes_per_launch": gemm_algorithmic_bytes(B, T),
         "flops_per_launch": gemm_fl / max(gemm_n, 1), "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
         "share_of_step": gemm_ms / prof_total if prof_total else None,
-        "breakdown_ms": {k: round(fam_ms[k], 3) for k in _lib.FAMILIES},
+        "breakdown_ms": {**{k: round(fam_ms[k], 3) for k in _lib.FAMILIES}, **{"codec_" + k: round(v, 3) for k, v in codec_ms.items()}},
         "breakdown_tflops": {k: (fl[k] / (fam_ms[k] * 1e-3) / 1e12 if fam_ms.get(k) else None) for k in fl},
         "profiled_step_ms": prof_total,
+        "secondary": secondary_rooflines(cfg, B, fam_ms, fam_n, fl, peaks, codec_ms),
     }
 
     if rank == 0:
-        tokens = world * B * T * 14 * args.steps
+        tokens = world * B * T * cfg["c_out"] * args.steps
         value = tokens / (ms * 1e-3)
+        flops_step = sum(fwd_flops(MODEL_CFG[tag], T) * steps_of[tag] for tag in stage_names) * B
+        if cfg["codec"]:
+            flops_step += B * (CODEC_FLOPS["encode"] + CODEC_FLOPS["decode"])
         line = {
-            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "metric": cfg["metric"], "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "rtf": world * B * T * HOP / SR * args.steps / (ms * 1e-3),
-            "tflops": world * (fwd_flops(COARSE, T) * COARSE_STEPS + fwd_flops(C2F, T) * C2F_STEPS) * B * args.steps
-                      / (ms * 1e-3) / 1e12,
-            "config": {"workload": "BASELINE.json configs[2]: coarse generate 12 steps (4 codebooks, 20 layers) -> c2f "
-                                   "generate 24 steps (14 codebooks, 16 layers), unchunked, d=1280, default sampling",
+            "tflops": world * flops_step * args.steps / (ms * 1e-3) / 1e12,
+            "config": {"workload": cfg["workload"], "baseline_config_index": args.config,
                        "global_batch": world * B, "per_gpu_batch": B, "seq_len": T, "parallelism": f"dp{world} (clips)",
-                       "l2": "working set per step (2.4 GB bf16 weights + >1 GB logits) far exceeds the 126 MB L2",
+                       "l2": "working set per step (1.3-2.4 GB bf16 weights + logits) far exceeds the 126 MB L2",
                        "weights": "random-init, NCCL-broadcast from rank 0", "cuda_graph": True},
             "clocks": clk,
             "e2e": {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms / args.steps,
-                    "api": "VampNet.generate(coarse) -> VampNet.generate(c2f) with pinned host tensors in, host tensor out"},
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms / args.steps, "api": api,
+                    "rtf": world * B * T * HOP / SR * args.steps / (e2e_ms * 1e-3)},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
-            v, parts = cpu_sample(threads)
-            line["cpu_baseline"] = {
-                "value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
-                "sample": (f"1 coarse + 1 c2f sampling iteration at B=1,T=768 via the oracle port (fp32): "
-                           f"{parts['coarse']:.2f}s + {parts['c2f']:.2f}s, extrapolated to 12+24 iterations per clip")}
+            v, parts = cpu_sample(threads, cfg)
+            line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                    "sample": cpu_sample_text(cfg, parts, threads)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -106,3 +106,42 @@ def test_full_path_encode_vamp_decode(iface):
     lat = torch.cat([w[f"quantizer.quantizers.{i}.codebook.weight"][z[:, i].cpu()].transpose(1, 2) for i in range(14)], 1)
     ref = do.decode(do.rvq_from_latents(lat, w, CODEC)[0], w, CODEC)["audio"]
     assert (out.samples.cpu() - ref).abs().max() < 5e-4
+
+
+def test_chunk_loops_do_not_synchronise(iface):
+    """between the first chunk's generate() and the end of coarse_vamp / coarse_to_fine nothing
+    may wait for the device (the reference syncs twice per chunk in apply_mask plus once for the edge-anchor test).
+    torch's sync debug mode turns any synchronising torch call into an error from the first chunk on."""
+    g = torch.Generator().manual_seed(3)
+    T = 83  # three coarse chunks (35 + 35 + 13), six c2f chunks of 15
+    z = torch.randint(0, 1024, (2, 14, T), generator=g).cuda()
+    mask = torch.ones_like(z)
+    mask[:, :, ::7] = 0
+    kw = dict(_sampling_steps=2, seed=1)
+    iface.coarse_vamp(z, mask, **kw)                      # warm: workspaces, graphs, packed weights
+    iface.coarse_to_fine(z, mask=mask, **kw)
+    torch.cuda.synchronize()
+    calls = []
+
+    def armed(fn):
+        def run(**k):
+            if not calls:
+                torch.cuda.set_sync_debug_mode("error")
+            calls.append(1)
+            return fn(**k)
+        return run
+
+    try:
+        out = iface.coarse_vamp(z, mask, gen_fn=armed(iface.coarse.generate), **kw)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert len(calls) == 3 and out.shape == z.shape
+    calls.clear()
+    orig = iface.c2f.generate
+    iface.c2f.generate = armed(orig)
+    try:
+        fine = iface.coarse_to_fine(z, mask=mask, **kw)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+        del iface.c2f.generate
+    assert len(calls) == 6 and fine.shape == z.shape

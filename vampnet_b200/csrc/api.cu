@@ -163,6 +163,7 @@ enum { FAM_EMBED = 0, FAM_RMSNORM, FAM_GEMM_QKV, FAM_ATTN, FAM_GEMM_O, FAM_GEMM_
        FAM_SAMPLE, FAM_STATE, FAM_COUNT };
 static unsigned long long g_captures = 0;  // generate graphs captured + instantiated so far
 static unsigned long long g_launches = 0;  // kernels launched by this library (graph replays add their node count)
+void count_launch(unsigned long long n) { g_launches += n; }
 struct Profiler {
   bool on = false;
   std::vector<cudaEvent_t> pool;

@@ -299,6 +299,7 @@ int32_t vnb_codec_conv1d(const float* x, const float* w, const float* bias, cons
                          int32_t out_off, int32_t nq, int32_t do_tanh, void* stream) {
   cudaError_t e = launch_conv1d(x, w, bias, snake_alpha, residual, y, B, Cin, Tin, Cout, Tout, K, stride, dil, pad,
                                 out_stride, out_off, nq, do_tanh, reinterpret_cast<cudaStream_t>(stream));
+  if (e == cudaSuccess) count_launch();
   return e == cudaSuccess ? 0 : vnb_set_error_cuda("vnb_codec_conv1d", static_cast<int>(e));
 }
 int32_t vnb_codec_rvq(int32_t mode, const float* in_f, const int64_t* in_codes, const float* win, const float* bin,
@@ -307,6 +308,7 @@ int32_t vnb_codec_rvq(int32_t mode, const float* in_f, const int64_t* in_codes, 
                       void* zq_hi, void* zq_lo, void* stream) {
   cudaError_t e = launch_rvq(mode, in_f, in_codes, win, bin, wout, bout, cb, cbn, codes, zq, latents, B, D, T, L, V,
                              reinterpret_cast<cudaStream_t>(stream), channels_last, zq_hi, zq_lo);
+  if (e == cudaSuccess) count_launch();
   return e == cudaSuccess ? 0 : vnb_set_error_cuda("vnb_codec_rvq", static_cast<int>(e));
 }
 }

@@ -324,6 +324,7 @@ int32_t vnb_codec_conv_tc(const void* a_hi, const void* a_lo, int32_t B, int32_t
   conv_tcgen05_kernel<<<tiles < sms ? tiles : sms, CT_THREADS, CT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
       tAh, tAl, tWh, tWl, g);
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch();
   return e == cudaSuccess ? 0 : vnb_set_error_cuda("conv_tcgen05_kernel launch", static_cast<int>(e));
 }
 
@@ -335,6 +336,7 @@ int32_t vnb_codec_conv_in(const float* x, const float* w, const float* bias, con
       x, w, bias, alpha, out_f32, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), B, T,
       C, K, pad);
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch();
   return e == cudaSuccess ? 0 : vnb_set_error_cuda("codec_in_kernel", static_cast<int>(e));
 }
 
@@ -350,6 +352,7 @@ int32_t vnb_codec_conv_out(const void* a_hi, const void* a_lo, const float* w, c
       reinterpret_cast<const __nv_bfloat16*>(a_hi), reinterpret_cast<const __nv_bfloat16*>(a_lo), w, bias, audio, B, T, C, K,
       pad);
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch();
   return e == cudaSuccess ? 0 : vnb_set_error_cuda("codec_out_kernel", static_cast<int>(e));
 }
 }

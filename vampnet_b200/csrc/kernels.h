@@ -28,6 +28,9 @@ inline int device_sm_count() {
   return sms[dev];
 }
 
+// kernels launched by this library so far (vnb_launch_count; graph replays add their node count)
+void count_launch(unsigned long long n = 1);
+
 // ---- TMA tensor maps (driver entry point fetched at run time; no link-time libcuda dependency) ----
 // 2-D bf16 row-major (rows, cols) with a (box_rows x 64) box, 128B swizzle.
 bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,

@@ -238,16 +238,19 @@ class Interface(torch.nn.Module):
         (interface.py:407-413).  Fine codebooks ride along untouched."""
         n_books = self.coarse.n_codebooks
         tokens, keep = z[:, :n_books, :].clone(), mask[:, :n_books, :]
+        assert keep.dtype == torch.long, f"mask must be long dtype, but got {keep.dtype}"
+        assert bool(((keep == 0) | (keep == 1)).all()), "mask must be binary"   # the one host sync of this call
         span = self.s2t(self.coarse.chunk_size_s)
         run = gen_fn or self.coarse.generate
         starts, results = [], []
         for lo, hi in self._spans(tokens.shape[-1], span):
-            m = keep[..., lo:hi]
-            if bool((m == 0).any()):
-                m = m.clone()
-                m[..., 0] = 0
-                m[..., -1] = 0
-            start, m = pmask.apply_mask(tokens[..., lo:hi], m, self.coarse.mask_token)
+            # a chunk that keeps anything also keeps its first and last frame; decided on the device (no sync):
+            # edge value = 0 where any(m == 0) else unchanged
+            m = keep[..., lo:hi].clone()
+            anchors = (m == 0).any()
+            m[..., 0] = torch.where(anchors, torch.zeros_like(m[..., 0]), m[..., 0])
+            m[..., -1] = torch.where(anchors, torch.zeros_like(m[..., -1]), m[..., -1])
+            start, m = pmask.apply_mask(tokens[..., lo:hi], m, self.coarse.mask_token, check=False)
             starts.append(start)
             results.append(run(codec=self.codec, time_steps=span, start_tokens=start, mask=m, return_signal=False,
                                **kwargs))
