@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define VNB_ABI_VERSION 1
+#define VNB_ABI_VERSION 2
 
 typedef struct vnb_model vnb_model;
 
@@ -39,9 +39,12 @@ typedef struct vnb_config {
  * side (vampnet_b200/modules/transformer.py: pack_weights). */
 typedef struct vnb_weights {
   const float* emb_table;  /* (C, V+1, 8)  codec codebooks with the learned MASK row appended (layers.py:145-150) */
-  const float* emb_wt;     /* (8C, d)      embedding.out_proj.weight transposed (layers.py:132) */
+  const void* emb_w3;      /* (d, 3*Kp)    bf16, embedding.out_proj.weight (d, 8C) zero-padded to Kp = 8C rounded up to 64
+                                           and split w = hi + lo: rows are [hi | lo | hi], the B operand of the
+                                           split-bf16 contraction [a_hi | a_hi | a_lo] . [w_hi | w_lo | w_hi]^T
+                                           (fp32-grade: the dropped a_lo.w_lo term is 2^-18 relative) (layers.py:132,162) */
   const float* emb_b;      /* (d) */
-  const float* norm1;      /* (L, d)       norm_1.weight (kept for vnb_op_rmsnorm; the forward uses the folded form) */
+  const float* norm1;      /* (L, d)       norm_1.weight (informational; the forward uses the folded form) */
   const void* wqkv;        /* (L, 3d, d)   bf16, rows = [w_qs | w_ks | w_vs] (transformer.py:109-114), columns scaled
                                            by norm_1.weight: RMSNorm (transformer.py:43-58) is fused, the kernels
                                            apply rsqrt(mean(x^2)+eps) as a row scale of the GEMM result */
@@ -146,15 +149,10 @@ enum {
  * N % 256 == 0, K % 64 == 0.  For VNB_EPI_QKV: out = qk, out2 = vT, T/Tpad describe the batch split. */
 int32_t vnb_op_gemm(int32_t epi, const void* A, const void* W, int32_t M, int32_t N, int32_t K, void* out,
                     void* out2, const float* bias, int32_t T, int32_t Tpad, void* stream);
-/* y bf16 = w * x * rsqrt(mean(x^2) + eps)  (transformer.py:43-58) */
-int32_t vnb_op_rmsnorm(const float* x, const float* w, void* y, int32_t M, int32_t d, float eps, void* stream);
 /* Fused self-attention with relative-position bias (transformer.py:234-254).
  * qk (B, T, 2d) bf16 [q | k], vT (B, d, Tpad) bf16, out (B, T, d) bf16, d = H*64. */
 int32_t vnb_op_attention(const void* qk, const void* vT, void* out, const float* rel_bias, int32_t rel_sat,
                          int32_t B, int32_t T, int32_t Tpad, int32_t H, void* stream);
-/* x fp32 (B*T, d) = out_proj(from_codes(codes)) ; codes_btc (B, T, C) int32 (internal layout). */
-int32_t vnb_op_embed_codes(const int32_t* codes_btc, const float* table, const float* wt, const float* b, float* x,
-                           int32_t B, int32_t T, int32_t C, int32_t V1, int32_t d, void* stream);
 /* Naive SIMT GEMM used only to bisect the tcgen05 path in tests: out fp32 (M, N) = A x W^T. */
 int32_t vnb_dbg_gemm_ref(const void* A, const void* W, int32_t M, int32_t N, int32_t K, float* out, void* stream);
 

@@ -15,7 +15,8 @@ def built():
 def test_library_loads_and_exports_header_symbols(built):
     from vampnet_b200 import _lib
     L = _lib.lib()
-    assert L.vnb_abi_version() == 1
+    header_version = int(re.search(r"#define VNB_ABI_VERSION (\d+)", open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "include", "vampnet_b200.h")).read()).group(1))
+    assert L.vnb_abi_version() == header_version == 2
     header = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "include", "vampnet_b200.h")).read()
     declared = set(re.findall(r"\b(vnb_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"

@@ -55,7 +55,11 @@ def test_pack_weights_layout_cpu():
     p = m.pack_weights(codec)
     d, V, Cp = 256, 1024, 10
     assert p["emb_table"].shape == (14, 1025, 8) and torch.equal(p["emb_table"][3, 1024], sd["embedding.special.MASK"][3])
-    assert p["emb_wt"].shape == (112, d)
+    assert p["emb_w3"].shape == (d, 3 * 128) and p["emb_w3"].dtype == torch.bfloat16
+    w = sd["embedding.out_proj.weight"].squeeze(-1)
+    hi, lo = p["emb_w3"][:, :112].float(), p["emb_w3"][:, 128:240].float()
+    assert torch.equal(p["emb_w3"][:, 256:368].float(), hi) and (hi + lo - w).abs().max() < 2e-5 * w.abs().max()
+    assert not p["emb_w3"][:, 112:128].any() and not p["emb_w3"][:, 240:256].any()
     n1 = sd["transformer.layers.0.norm_1.weight"]
     wq = vo.fold_lora(sd, "transformer.layers.0.self_attn.w_qs") * n1[None, :]
     assert torch.equal(p["wqkv"][0, :d], wq.to(torch.bfloat16))

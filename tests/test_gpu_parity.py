@@ -336,3 +336,28 @@ def test_broadcastable_mask_and_flash_checkpoint_rejected():
     bad["transformer.layers.0.self_attn.Wqkv.weight"] = torch.zeros(3 * cfg.embedding_dim, cfg.embedding_dim)
     with pytest.raises(RuntimeError, match="FlashMHA"):
         model.load_state_dict(bad, strict=False)
+
+
+def test_embedding_projection_is_fp32_grade():
+    """CodebookEmbedding.from_codes + out_proj (reference layers.py:134-162) runs as a split-bf16 tensor-core
+    contraction; with the transformer stack switched off (zero layers cannot be built, so: compare the residual stream
+    tap of a model whose layers contribute exactly zero) it must match the fp32 einsum to ~1e-5 relative."""
+    cfg, sd, model, cb, codec = build(TINY_C2F, seed=4)
+    sd = dict(sd)
+    for k in list(sd):  # zero every projection that feeds the residual stream: x stays the embedding
+        if k.endswith("self_attn.fc.weight") or k.endswith("feed_forward.w_2.weight"):
+            sd[k] = torch.zeros_like(sd[k])
+    model.load_state_dict(sd, strict=False)
+    g = torch.Generator().manual_seed(8)
+    z = torch.randint(0, 1025, (2, cfg.n_codebooks, 37), generator=g)
+    model.forward_codes(z.cuda(), codec)
+    x = model.hidden_state(2, 37).cpu()
+    orc = vo.OracleVampNet(cfg, sd, "fp32")
+    lat = orc.from_codes(z, cb)
+    want = torch.einsum("bkt,nk->btn", lat, orc.emb_w) + orc.emb_b
+    err = (x - want).abs().max().item()
+    print(f"embedding projection: max err {err:.2e} on values of magnitude {want.abs().max():.2f}")
+    assert err < 3e-5 * max(1.0, want.abs().max().item())
+    # the latents entry point shares the contraction: bit-identical
+    model(lat.cuda())
+    assert torch.equal(model.hidden_state(2, 37).cpu(), x)

@@ -2,7 +2,7 @@
 statistics against a plain torch computation.  Each stage runs in its own process (tools/gpu_diag.sh)
 so that a trapping kernel cannot poison the others.
 
-    python tools/gpu_diag.py <stage>      stage in: gemm_small gemm_epi gemm_big rmsnorm attention embed sample
+    python tools/gpu_diag.py <stage>      stage in: gemm_small gemm_epi gemm_big attention codec attention_b32
 """
 import math
 import os
@@ -195,16 +195,6 @@ def main():
         run_gemm(24576, 5120, 1280, L.EPI_BF16, timing=True)
         run_gemm(6144, 5120, 1280, L.EPI_GEGLU)
         run_gemm(8 * 768, 3840, 1280, L.EPI_QKV, T=768)
-    elif stage == "rmsnorm":
-        lib = L.lib()
-        for M, d in ((5, 256), (4600, 1280)):
-            x = torch.randn(M, d, device=dev) * 3
-            w = 1 + 0.1 * torch.randn(d, device=dev)
-            y = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
-            L.check(lib.vnb_op_rmsnorm(L.ptr(x), L.ptr(w), L.ptr(y), M, d, 1e-6, L.stream_ptr()))
-            torch.cuda.synchronize()
-            ref = w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6))
-            stats(f"rmsnorm M={M} d={d}", y, ref.to(torch.bfloat16))
     elif stage == "attention":
         run_attention(1, 64, 1)
         run_attention(1, 128, 2)

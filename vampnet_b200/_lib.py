@@ -23,7 +23,7 @@ class Config(C.Structure):
 
 class Weights(C.Structure):
     _fields_ = [
-        ("emb_table", C.c_void_p), ("emb_wt", C.c_void_p), ("emb_b", C.c_void_p), ("norm1", C.c_void_p),
+        ("emb_table", C.c_void_p), ("emb_w3", C.c_void_p), ("emb_b", C.c_void_p), ("norm1", C.c_void_p),
         ("wqkv", C.c_void_p), ("wo", C.c_void_p), ("norm3", C.c_void_p), ("w1", C.c_void_p), ("w2", C.c_void_p),
         ("norm_f", C.c_void_p), ("wcls", C.c_void_p), ("bcls", C.c_void_p), ("rel_bias", C.c_void_p),
         ("rel_sat", C.c_int32),
@@ -61,11 +61,8 @@ _SIGS = {
                                     C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]),
     "vnb_op_gemm": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
-    "vnb_op_rmsnorm": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "vnb_op_attention": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_void_p]),
-    "vnb_op_embed_codes": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vnb_codec_conv1d": (C.c_int32, [C.c_void_p] * 6 + [C.c_int32] * 13 + [C.c_void_p]),
     "vnb_codec_rvq": (C.c_int32, [C.c_int32] + [C.c_void_p] * 11 + [C.c_int32] * 6 + [C.c_void_p] * 3),
     "vnb_codec_conv_tc": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
@@ -104,7 +101,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.vnb_abi_version() != 1:
+    if L.vnb_abi_version() != 2:
         raise RuntimeError("ABI version mismatch between _lib.py and libvampnet_b200.so")
     _lib = L
     return L

@@ -146,10 +146,11 @@ struct GraphKey {  // graphs bake pointers, so generate() stages z/mask/out in w
 struct Workspace {
   int B = 0, T = 0, Tpad = 0, M = 0;
   unsigned long long last_use = 0;
-  DevBuf x, y, qk, vT, att, h, logits, zcur, zorig, tokens, conf, n0, dyn, z_in, mask_in, z_out, ssA, ssB;
+  DevBuf x, y, qk, vT, att, h, logits, zcur, zorig, tokens, conf, n0, dyn, z_in, mask_in, z_out, ssA, ssB, embA;
+  int embKp = 0;
   int ss_parts = 0;
   std::vector<GemmPlan> qkv, wo, up, down;
-  GemmPlan cls;
+  GemmPlan cls, emb;
   AttnPlan attn;
   std::map<GraphKey, cudaGraphExec_t> graphs;
   std::map<GraphKey, unsigned long long> graph_kernels;
@@ -221,6 +222,8 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   ws->ss_parts = 2 * (d / 256);  // two partial row-sums-of-squares (even / odd chunks) per 256-column tile of the producing GEMM
   CK(ws->ssA.alloc(M * ws->ss_parts * 4, true));
   CK(ws->ssB.alloc(M * ws->ss_parts * 4, true));
+  ws->embKp = (c.n_codebooks * 8 + 63) / 64 * 64;                 // gathered latents [hi | hi | lo], each third padded to Kp
+  CK(ws->embA.alloc(M * 3 * ws->embKp * 2));
   CK(ws->qk.alloc(M * 2 * d * 2));
   CK(ws->vT.alloc(static_cast<size_t>(B) * d * ws->Tpad * 2, /*zero=*/true));  // padding keys stay 0 forever
   CK(ws->att.alloc(M * d * 2));
@@ -263,6 +266,12 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
                       m->w.bcls, T, ws->Tpad, 0))
     return fail("plan classifier: %s", tmap_error());
   consumer(ws->cls, ws->ssA);
+  // embedding out_proj (layers.py:162) as a split-bf16 tensor-core contraction: x = A . emb_w3^T + bias, which also
+  // emits bf16(x) and the row sums of squares the first QKV projection's fused RMSNorm consumes
+  if (!make_gemm_plan(&ws->emb, VNB_EPI_BIAS_F32, ws->embA.p, m->w.emb_w3, ws->M, d, 3 * ws->embKp, ws->x.p, nullptr,
+                      m->w.emb_b, T, ws->Tpad, 0) ||
+      !gemm_plan_set_fused_out(&ws->emb, ws->y.p, ws->ssA.as<float>()))
+    return fail("plan embedding: %s", tmap_error());
   if (!make_attn_plan(&ws->attn, ws->qk.p, ws->vT.p, ws->att.p, m->w.rel_bias, m->w.rel_sat, B, T, ws->Tpad, c.n_heads))
     return fail("plan attention: %s", tmap_error());
   ws->last_use = ++m->use_clock;
@@ -277,6 +286,16 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
     CK(expr);                     \
     ++g_launches;                 \
   } while (0)
+
+// CodebookEmbedding (layers.py:134-162): gather (+ split) the latents, then the out_proj contraction on the tensor cores.
+static int run_embed(vnb_model* m, Workspace* ws, const int32_t* codes_btc, const float* latents, cudaStream_t st) {
+  const vnb_config& c = m->cfg;
+  LAUNCH(FAM_EMBED, launch_embed_gather(codes_btc, latents, m->w.emb_table, ws->embA.p, ws->M, ws->T, c.n_codebooks,
+                                        c.vocab_size + 1, c.n_codebooks * 8, ws->embKp, ws->ssA.as<float>(),
+                                        c.d_model / 256, ws->ss_parts, st));
+  LAUNCH(FAM_EMBED, launch_gemm(ws->emb, st));
+  return 0;
+}
 
 // x already holds the embedded input; runs the L layers + final norm + classifier into `logits`.
 static int run_stack(vnb_model* m, Workspace* ws, float* logits, cudaStream_t st, float* acts = nullptr) {
@@ -342,8 +361,7 @@ int32_t vnb_forward_codes(vnb_model* m, const int64_t* codes, int32_t B, int32_t
   // (B,C,T) int64 -> (B,T,C) int32, no masking (mask = zeros)
   LAUNCH(FAM_STATE, launch_gen_init(codes, nullptr, ws->zcur.as<int32_t>(), ws->zorig.as<int32_t>(), ws->n0.as<int32_t>(), B,
                      c.n_codebooks, T, /*ncc=*/c.n_codebooks, c.vocab_size, st));
-  LAUNCH(FAM_EMBED, launch_embed_codes(ws->zcur.as<int32_t>(), m->w.emb_table, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), ws->M,
-                        c.n_codebooks, c.vocab_size + 1, c.d_model, st, ws->y.p, ws->ssA.as<float>(), ws->ss_parts));
+  if (run_embed(m, ws, ws->zcur.as<int32_t>(), nullptr, st)) return 1;
   m->last = ws;
   return run_stack(m, ws, logits, st);
 }
@@ -352,9 +370,7 @@ int32_t vnb_forward_latents(vnb_model* m, const float* latents, int32_t B, int32
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   Workspace* ws;
   if (get_workspace(m, B, T, &ws)) return 1;
-  const vnb_config& c = m->cfg;
-  LAUNCH(FAM_EMBED, launch_embed_latents(latents, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), B, T, c.n_codebooks * 8, c.d_model, st,
-                                          ws->y.p, ws->ssA.as<float>(), ws->ss_parts));
+  if (run_embed(m, ws, nullptr, latents, st)) return 1;
   m->last = ws;
   return run_stack(m, ws, logits, st);
 }
@@ -364,9 +380,7 @@ int32_t vnb_forward_latents_acts(vnb_model* m, const float* latents, int32_t B, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   Workspace* ws;
   if (get_workspace(m, B, T, &ws)) return 1;
-  const vnb_config& c = m->cfg;
-  LAUNCH(FAM_EMBED, launch_embed_latents(latents, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), B, T, c.n_codebooks * 8, c.d_model, st,
-                                          ws->y.p, ws->ssA.as<float>(), ws->ss_parts));
+  if (run_embed(m, ws, nullptr, latents, st)) return 1;
   m->last = ws;
   return run_stack(m, ws, logits, st, acts);
 }
@@ -392,8 +406,7 @@ static int enqueue_generate(vnb_model* m, Workspace* ws, const int64_t* z, const
   sa.n0 = ws->n0.as<int32_t>();
   sa.B = ws->B; sa.T = ws->T; sa.C = c.n_codebooks; sa.ncc = ncc; sa.V = c.vocab_size; sa.mask_token = c.vocab_size;
   for (int i = 0; i < steps; ++i) {
-    LAUNCH(FAM_EMBED, launch_embed_codes(ws->zcur.as<int32_t>(), m->w.emb_table, m->w.emb_wt, m->w.emb_b, ws->x.as<float>(), ws->M,
-                          c.n_codebooks, c.vocab_size + 1, c.d_model, st, ws->y.p, ws->ssA.as<float>(), ws->ss_parts));
+    if (run_embed(m, ws, ws->zcur.as<int32_t>(), nullptr, st)) return 1;
     if (run_stack(m, ws, ws->logits.as<float>(), st)) return 1;
     LAUNCH(FAM_SAMPLE, launch_sample_step_dev(sa, ws->dyn.as<SampleDyn>() + i, st, use_top_p));
     ++g_launches;  // sample step = two kernels
@@ -551,20 +564,11 @@ int32_t vnb_op_gemm(int32_t epi, const void* A, const void* W, int32_t M, int32_
   CK(launch_gemm(p, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
-int32_t vnb_op_rmsnorm(const float* x, const float* w, void* y, int32_t M, int32_t d, float eps, void* stream) {
-  CK(launch_rmsnorm(x, w, y, M, d, eps, reinterpret_cast<cudaStream_t>(stream)));
-  return 0;
-}
 int32_t vnb_op_attention(const void* qk, const void* vT, void* out, const float* rel_bias, int32_t rel_sat, int32_t B,
                          int32_t T, int32_t Tpad, int32_t H, void* stream) {
   AttnPlan p;
   if (!make_attn_plan(&p, qk, vT, out, rel_bias, rel_sat, B, T, Tpad, H)) return fail("attn plan: %s", tmap_error());
   CK(launch_attention(p, reinterpret_cast<cudaStream_t>(stream)));
-  return 0;
-}
-int32_t vnb_op_embed_codes(const int32_t* codes_btc, const float* table, const float* wt, const float* b, float* x,
-                           int32_t B, int32_t T, int32_t C, int32_t V1, int32_t d, void* stream) {
-  CK(launch_embed_codes(codes_btc, table, wt, b, x, B * T, C, V1, d, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 int32_t vnb_dbg_gemm_ref(const void* A, const void* W, int32_t M, int32_t N, int32_t K, float* out, void* stream) {

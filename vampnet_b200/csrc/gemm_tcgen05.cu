@@ -355,7 +355,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else if constexpr (EPI == VNB_EPI_RESID || EPI == VNB_EPI_BIAS_F32) {
         // software-pipelined: the residual rows of chunk c+1 are in flight while chunk c is pulled out of TMEM,
         // transposed and stored (the global-load latency would otherwise be paid 8 times per tile, serially)
-        const bool fused_out = (EPI == VNB_EPI_RESID) && g.out_bf16 != nullptr;
+        const bool fused_out = g.out_bf16 != nullptr;  // residual GEMMs, and the embedding projection (BIAS_F32)
         constexpr int CSTEP = kWide ? 2 : 1;  // chunks owned by this warp: half, half + CSTEP, ...
         float ssacc[8];
 #pragma unroll

@@ -85,15 +85,10 @@ bool make_attn_plan(AttnPlan* p, const void* qk, const void* vT, void* out, cons
 cudaError_t launch_attention(const AttnPlan& p, cudaStream_t st);
 
 // ---- elementwise / gather ----
-cudaError_t launch_rmsnorm(const float* x, const float* w, void* y_bf16, int M, int d, float eps, cudaStream_t st);
-// codes_btc (B*T, C) int32  -> x (B*T, d) fp32
-// xb (bf16 copy of x) and ss (parts, M) row sums of squares (total in part 0, zeros elsewhere) are optional
-cudaError_t launch_embed_codes(const int32_t* codes_btc, const float* table, const float* wt, const float* b, float* x,
-                               int M, int C, int V1, int d, cudaStream_t st, void* xb = nullptr, float* ss = nullptr,
-                               int ss_parts = 0);
-// latents (B, K, T) fp32 -> x (B*T, d) fp32
-cudaError_t launch_embed_latents(const float* lat, const float* wt, const float* b, float* x, int B, int T, int K,
-                                 int d, cudaStream_t st, void* xb = nullptr, float* ss = nullptr, int ss_parts = 0);
+// codes_btc (B*T, C) int32 (or latents (B, K, T) fp32 when codes_btc is null) -> A (M, 3*Kp) bf16 = [hi | hi | lo] of the
+// gathered latents, the A operand of the out_proj contraction; zeroes ss partials [zero_from, ss_parts) of every row
+cudaError_t launch_embed_gather(const int32_t* codes_btc, const float* latents, const float* table, void* A, int M, int T,
+                                int C, int V1, int K, int Kp, float* ss, int zero_from, int ss_parts, cudaStream_t st);
 
 // ---- generate-loop state kernels ----
 // z (B,C,T) int64, mask (B,C,T) int32|null -> zcur (B,T,C) int32 (masked), zorig (B,T,C) int32; n0 += count(MASK)

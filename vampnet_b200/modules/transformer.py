@@ -331,7 +331,15 @@ class VampNet(nn.Module):
         bf = torch.bfloat16
         p = {}
         p["emb_table"] = self.embedding.lookup_tables(codec).to(dev).contiguous()
-        p["emb_wt"] = self.embedding.out_proj.weight.float().squeeze(-1).t().contiguous()
+        # out_proj as a tensor-core contraction with fp32-grade accuracy: w = hi + lo in bf16, K padded to a multiple of
+        # 64, rows [hi | lo | hi] against the gathered latents [a_hi | a_hi | a_lo] (vnb_weights.emb_w3)
+        w = self.embedding.out_proj.weight.float().squeeze(-1)                      # (d, 8C)
+        kp = (w.shape[1] + 63) // 64 * 64
+        wp = torch.zeros(d, kp, device=w.device, dtype=torch.float32)
+        wp[:, :w.shape[1]] = w
+        hi = wp.to(bf)
+        lo = (wp - hi.float()).to(bf)
+        p["emb_w3"] = torch.cat([hi, lo, hi], dim=1).contiguous()                   # (d, 3*Kp)
         p["emb_b"] = self.embedding.out_proj.bias.float().contiguous()
         lay = self.transformer.layers
         p["norm1"] = torch.stack([l.norm_1.weight.float() for l in lay]).contiguous()
@@ -382,7 +390,7 @@ class VampNet(nn.Module):
             cfg = _lib.Config(self.n_heads, self.n_layers, self.n_codebooks, self.n_conditioning_codebooks,
                               self.latent_dim, self.embedding_dim, self.vocab_size)
             w = _lib.Weights()
-            for name in ("emb_table", "emb_wt", "emb_b", "norm1", "wqkv", "wo", "norm3", "w1", "w2", "norm_f", "wcls",
+            for name in ("emb_table", "emb_w3", "emb_b", "norm1", "wqkv", "wo", "norm3", "w1", "w2", "norm_f", "wcls",
                          "bcls", "rel_bias"):
                 setattr(w, name, p[name].data_ptr())
             w.rel_sat = self._rel_sat
