@@ -92,10 +92,9 @@ def gemm_algorithmic_bytes(B, T, d=1280):
 
 def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch from the committed `ncu --set full` summary
-    (profiles/ncu_gemm_r1_final.txt: one layer's qkv / attn-out / ffn-up / ffn-down at the bench shape)."""
-    name = "ncu_gemm_r1_pair.txt"  # CTA-pair kernel (current default); older capture of the single-CTA kernel otherwise
-    if not os.path.exists(os.path.join(ROOT, "profiles", name)):
-        name = "ncu_gemm_r1_final.txt"
+    (profiles/ncu_layer_r2.txt: one layer's qkv / attn-out / ffn-up / ffn-down at the bench shape)."""
+    name = next((n for n in ("ncu_layer_r2.txt", "ncu_gemm_r1_pair.txt", "ncu_gemm_r1_final.txt")
+                 if os.path.exists(os.path.join(ROOT, "profiles", n))), "ncu_layer_r2.txt")
     path = os.path.join(ROOT, "profiles", name)
     try:
         per_kind, cur = {}, None
