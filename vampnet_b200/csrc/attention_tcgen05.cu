@@ -22,6 +22,11 @@
 // once per block, and only when a row grew by more than 2^8 is the reference moved, O and l rescaled and the block's P
 // recomputed from the score tile (still in TMEM: it is released together with P).
 //
+// A persistent variant (CTAs walking work items, next item's Q prefetched, first Q.K^T of the next item overlapping the
+// O write-back) was measured too: correct, but 207 us at T=768 and 686 us at T=3072 — SLOWER than one item per CTA (the
+// hardware's dynamic CTA dispatch balances the two co-resident CTAs of an SM better than a static item walk, and 1920
+// items over 296 resident CTAs quantise to 7 vs 6.49 rounds), so the grid stays (query tile, head, batch).
+//
 // Measured on B200 at B=32, T=768, H=20 (profiles/attention_r2_variants.txt): this kernel 198 us (489 TFLOP/s); the round-1
 // kernel (two-phase, P through shared memory) 222 us; P through TMEM alone 205 us; two 128-query tiles per CTA with
 // 128-key blocks 240-258 us; evaluating 25-50 % of the exponentials as a cubic polynomial on the FMA pipe did not help
@@ -153,10 +158,8 @@ struct Softmax {
     if (j == 0) {  // no reference yet: a max-only pass over block 0 sets it (use 0 of the exchange slots)
       m_ref = row_max(0, pass<false>(0, sn, pk));
     }
-    if (j >= 2) {  // P[j&1] was last read by the P.V of block j-2 (long retired)
-      mbar_wait_a(sb + BAR_P_FREE + 8 * jb, ((j - 2) >> 1) & 1, 755);
-      tc_fence_after();
-    }
+    // P[j&1] is free: it was last read by the P.V of block j-2, and Q.K^T of block j (whose completion was just
+    // waited for) was issued after that P.V on the in-order tensor pipe — no separate barrier wait needed.
     psum2[0] = pack2(0.f, 0.f);
     psum2[1] = pack2(0.f, 0.f);
     const float mx = row_max(j + 1, pass<true>(j, sn, pk));
