@@ -227,7 +227,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
-  else __syncthreads();
+  __syncthreads();  // (pair: redundant after the cluster barrier, but it is the barrier compute-sanitizer's racecheck
+                    //  understands between tcgen05.alloc's write of tmem_slot and the reads below)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
