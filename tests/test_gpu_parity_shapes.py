@@ -114,21 +114,27 @@ def test_greedy_generate_six_steps_agreement_floor(path):
     assert agree >= 0.85
 
 
-def _calibrated_compare(cfg, sd, got_rows, lat_rows, tag):
+def _calibrated_compare(cfg, sd, got_rows, lat_rows, tag, floor_caps=None):
     """got_rows[i] (V, S) from the GPU for latents lat_rows[i] (1, K, T): distance to the bf16 oracle, required to be
-    within 1.5x of the oracle's own jitter floor on the same inputs; decisions exact where the fp32 margin is safe."""
+    within 1.5x of the oracle's own jitter floor on the same inputs (or, with floor_caps = (max, mean), of the floor
+    measured for this model at shorter T: saves the third 25 s oracle forward at T = 3072); decisions exact where the
+    fp32 margin is safe."""
     orc_bf16 = vo.OracleVampNet(cfg, sd, "bf16")
-    orc_jit = vo.OracleVampNet(cfg, sd, "bf16", jitter=1e-6, jitter_seed=1)
+    orc_jit = vo.OracleVampNet(cfg, sd, "bf16", jitter=1e-6, jitter_seed=1) if floor_caps is None else None
     orc_32 = vo.OracleVampNet(cfg, sd, "fp32")
     for i, (got, lat) in enumerate(zip(got_rows, lat_rows)):
         t0 = time.time()
         ref = orc_bf16.forward(lat)[0]
-        jit = orc_jit.forward(lat)[0]
         ref32 = orc_32.forward(lat)[0]
-        floor, e = (jit - ref).abs(), (got - ref).abs()
+        e = (got - ref).abs()
+        if orc_jit is not None:
+            floor = (orc_jit.forward(lat)[0] - ref).abs()
+            fmax, fmean = floor.max().item(), floor.mean().item()
+        else:
+            fmax, fmean = floor_caps
         print(f"[{tag} row {i}] vs bf16 oracle: max {e.max():.3e} mean {e.mean():.3e}; oracle jitter floor: max "
-              f"{floor.max():.3e} mean {floor.mean():.3e}  (3 oracle forwards: {time.time() - t0:.1f} s)")
-        assert e.mean() <= 1.5 * floor.mean() and e.max() <= 1.5 * floor.max() + 5e-3
+              f"{fmax:.3e} mean {fmean:.3e}  (oracle forwards: {time.time() - t0:.1f} s)")
+        assert e.mean() <= 1.5 * fmean and e.max() <= 1.5 * fmax + 5e-3
         assert_decisions_exact_where_margin_allows(got.t()[None], ref32.t()[None], f"{tag} row {i}")
 
 
@@ -176,4 +182,6 @@ def test_full_coarse_forward_long_context():
     z[:, :, ::4] = 1024
     got = model.forward_codes(z.cuda(), codec)
     orc = vo.OracleVampNet(cfg, sd, "fp32")
-    _calibrated_compare(cfg, sd, [got[1].t().cpu()], [orc.from_codes(z[1:2], cb)], f"coarse B={B} T={T}")
+    # jitter floor of this model measured at T=768 (3.2-3.6e-2 max / 4.4-4.5e-3 mean) and at T=3072 (3.8e-2 / 4.8e-3)
+    _calibrated_compare(cfg, sd, [got[1].t().cpu()], [orc.from_codes(z[1:2], cb)], f"coarse B={B} T={T}",
+                        floor_caps=(3.8e-2, 4.8e-3))
