@@ -104,7 +104,7 @@ class AudioSignal:
         x = self.audio_data
         B, Cn, N = x.shape
         zeros = 24
-        cutoff = 0.945 / max(up, down)
+        cutoff = 0.5 * 0.945 / max(up, down)  # cycles/sample at the up-sampled rate: 94.5 % of the lower Nyquist
         half = zeros * max(up, down)
         t = torch.arange(-half, half + 1, device=x.device, dtype=torch.float64)
         h = 2 * cutoff * torch.sinc(2 * cutoff * t) * torch.kaiser_window(2 * half + 1, periodic=False, beta=8.6,
