@@ -27,7 +27,10 @@
 // hardware's dynamic CTA dispatch balances the two co-resident CTAs of an SM better than a static item walk, and 1920
 // items over 296 resident CTAs quantise to 7 vs 6.49 rounds), so the grid stays (query tile, head, batch).
 //
-// Measured on B200 at B=32, T=768, H=20 (profiles/attention_r2_variants.txt): this kernel 198 us (489 TFLOP/s); the round-1
+// Likewise 128-key blocks with a single score buffer (all that fits next to O and P in 256 TMEM columns): 202 / 615 us.
+//
+// Measured on B200 at B=32, T=768, H=20 (profiles/attention_r2_variants.txt): this kernel 190.5 us (507 TFLOP/s; T=3072,
+// B=8: 573 us, 674 TFLOP/s); the round-1
 // kernel (two-phase, P through shared memory) 222 us; P through TMEM alone 205 us; two 128-query tiles per CTA with
 // 128-key blocks 240-258 us; evaluating 25-50 % of the exponentials as a cubic polynomial on the FMA pipe did not help
 // in any of them (the kernels are issue/latency-bound at 20 warps per SM, not MUFU-bound), so that path was removed.
