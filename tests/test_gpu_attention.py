@@ -77,17 +77,23 @@ def test_attention_saturated_table_matches_unsaturated_lookup(L):
     assert torch.equal(a, b)
 
 
-def test_attention_reference_moves_when_logits_grow(L):
-    """Scores with a wide dynamic range force the rescale path: the row maximum of later key blocks exceeds the
-    reference set by block 0 by far more than 2^8, so O and l are rescaled and the block's P recomputed."""
+@pytest.mark.parametrize("first,later", [(1.0, 40.0), (40.0, 1.0), (40.0, 160.0)])
+def test_attention_reference_moves_when_logits_grow(L, first, later):
+    """The optimistic softmax takes block 0's row maximum as its reference and moves it only when a later block
+    outgrows it by more than 2^8.  Keys scaled so that (a) later blocks outgrow the reference by far more than that
+    (O and l rescaled, the block's P recomputed), (b) block 0 dominates and everything later underflows against it,
+    (c) both.  Optimistic exponentials overflow to inf in (a) and (c) before they are discarded; none of it may reach
+    the output."""
     B, T, H = 1, 640, 2
     q, k, v, rel, sat, qk, vT, Tpad = attention_inputs(B, T, H, seed=5)
     qk = qk.clone()
-    qk[:, 400:, H * 64:] *= 6.0   # keys of the later blocks produce much larger scores
+    qk[:, :64, H * 64:] *= first     # keys of block 0
+    qk[:, 400:, H * 64:] *= later    # keys of the later blocks
     got = run_attention(L, qk, vT, rel, sat, B, T, Tpad, H)
     d = H * 64
     ref = attention_ref(qk[..., :d], qk[..., d:], v, rel, sat, H)
     err = (got.float() - ref).abs()
+    assert not torch.isnan(got.float()).any()
     assert bool((err <= 2.0 ** -7 * ref.abs() + 8e-3).all()), err.max().item()
 
 
