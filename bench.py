@@ -306,11 +306,27 @@ def secondary_rooflines(cfg, B, fam_ms, fam_n, fl, peaks, codec_ms):
         logit_bytes += steps * B * T * Cp * 1024 * 4.0                        # fp32 logits read once per iteration
         emb_bytes += steps * B * T * (Cn * (4 + 32) + d * (4 + 2) + 8)        # codes + table rows in, x fp32 + bf16 copy out
     if fam_ms.get("sample_remask"):
-        a = logit_bytes / (fam_ms["sample_remask"] * 1e-3) / 1e9
-        out.append({"kernel": "sample_rows_kernel + remask_kernel", "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s",
-                    "frac": a / hbm, "algorithmic_bytes_per_step": logit_bytes, "ms_per_step": fam_ms["sample_remask"],
-                    "note": "contract figure: every fp32 logit read once (SURVEY.md 8d); positions already known are "
-                            "skipped by the kernel, so the bytes actually moved are fewer"})
+        from vampnet_b200 import _lib
+        import ctypes
+        v = ctypes.c_int32(0)
+        _lib.lib().vnb_get_option(b"fused_sampler", ctypes.byref(v))
+        if v.value:
+            # the sampling sweeps run in the classifier GEMM's epilogue (counted under gemm_classifier); what is left
+            # here reads 16 bytes per (position, 128-entry vocabulary tile) and writes token + confidence
+            rec_bytes = logit_bytes / (128 * 4.0) * 16.0 + logit_bytes / (1024 * 4.0) * 12.0
+            a = rec_bytes / (fam_ms["sample_remask"] * 1e-3) / 1e9
+            out.append({"kernel": "sample_combine_kernel + remask_kernel (sampler fused into the classifier epilogue)",
+                        "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s", "frac": a / hbm,
+                        "algorithmic_bytes_per_step": rec_bytes, "ms_per_step": fam_ms["sample_remask"],
+                        "logit_bytes_not_moved_per_step": 2 * logit_bytes,
+                        "note": "latency-bound tail of the fused sampler: the fp32 logits (written and read once per "
+                                "iteration before) no longer reach HBM; one thread per position, 4-pass radix select per clip"})
+        else:
+            a = logit_bytes / (fam_ms["sample_remask"] * 1e-3) / 1e9
+            out.append({"kernel": "sample_rows_kernel + remask_kernel", "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s",
+                        "frac": a / hbm, "algorithmic_bytes_per_step": logit_bytes, "ms_per_step": fam_ms["sample_remask"],
+                        "note": "contract figure: every fp32 logit read once (SURVEY.md 8d); positions already known are "
+                                "skipped by the kernel, so the bytes actually moved are fewer"})
     if fam_ms.get("embed"):
         a = emb_bytes / (fam_ms["embed"] * 1e-3) / 1e9
         out.append({"kernel": "embed (codes -> residual stream)", "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s",

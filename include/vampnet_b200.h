@@ -131,6 +131,9 @@ uint64_t vnb_graph_capture_count(void);
  *              half of the weight tile), 0 = one CTA per 128 x 256 tile.  Results are bit-identical (same
  *              accumulation order per output element).  Initial value: environment VNB_GEMM_PAIR, else the
  *              compiled default.  Generate graphs are cached per value.
+ * "fused_sampler": 1 (default) = vnb_generate samples inside the classifier GEMM's epilogue (VNB_EPI_SAMPLE: the logits of
+ *   the generate loop never reach HBM), 0 = from a materialised fp32 logits tensor (sample_rows_kernel).  Both draw
+ *   with the same two-level inverse CDF and the same Philox stream; nucleus (top-p) sampling always materialises.
  * "gemm_pair_max_clusters" (get only): CTA pairs that can be co-resident on the current device. */
 int32_t vnb_set_option(const char* name, int32_t value);
 int32_t vnb_get_option(const char* name, int32_t* value);
@@ -143,7 +146,9 @@ enum {
   VNB_EPI_QKV = 1,      /* cols < 2d -> qk bf16 (M, 2d); cols >= 2d -> vT bf16 (B, d, Tpad) */
   VNB_EPI_RESID = 2,    /* out fp32 (M, N) += acc */
   VNB_EPI_GEGLU = 3,    /* out bf16 (M, N/2) = value * gelu_tanh(gate) */
-  VNB_EPI_BIAS_F32 = 4  /* out fp32 (M, N) = acc + bias[n] */
+  VNB_EPI_BIAS_F32 = 4, /* out fp32 (M, N) = acc + bias[n] */
+  VNB_EPI_SAMPLE = 5    /* internal to vnb_generate: acc + bias[n] sampled per 128-column strip, nothing stored but
+                           16 bytes per (row, strip); not accepted by vnb_op_gemm */
 };
 /* out = A (M,K) bf16 row-major  x  W (N,K)^T bf16 row-major, fp32 accumulate in TMEM.
  * N % 256 == 0, K % 64 == 0.  For VNB_EPI_QKV: out = qk, out2 = vT, T/Tpad describe the batch split. */

@@ -8,7 +8,8 @@ custom kernel, so parity under sampling is defined against this shared stream
 (SURVEY.md §7 "RNG parity").
 
 Stream layout (must match sampler.cu):
-  token noise  : counter = (s, b, step, 0), output lane 0   (ONE uniform per row: inverse-CDF draw)
+  token noise  : counter = (s, b, step, 0), output lanes 0 and 1   (TWO uniforms per row: a two-level inverse-CDF
+                 draw, lane 0 picks the 128-entry vocabulary tile, lane 1 the entry inside it)
   remask noise : counter = (s, b, step, 1), output lane 0
   key          = (seed_lo, seed_hi)
   uniform      = ((x >> 9) + 0.5) * 2**-23     -> strictly inside (0, 1), exact in fp32
@@ -62,9 +63,9 @@ def uniform_bsv(key, step: int, B: int, S: int, V: int) -> np.ndarray:
     return u.reshape(B, S, V)
 
 
-def uniform_bs(key, step: int, B: int, S: int, stream: int = 1) -> np.ndarray:
-    """(B, S) fp32 uniforms: stream 1 = re-mask Gumbel noise, stream 0 = categorical draw."""
+def uniform_bs(key, step: int, B: int, S: int, stream: int = 1, word: int = 0) -> np.ndarray:
+    """(B, S) fp32 uniforms: stream 1 = re-mask Gumbel noise, stream 0 = categorical draw (words 0 and 1)."""
     s = np.arange(S, dtype=np.uint32)[None, :]
     b = np.arange(B, dtype=np.uint32)[:, None]
     o = philox4x32_10(s, b, np.uint32(step), np.uint32(stream), key[0], key[1])
-    return to_uniform(o[0])
+    return to_uniform(o[word])

@@ -324,18 +324,28 @@ class OracleVampNet:
         elif rng == "torch":
             token = probs.view(-1, V).multinomial(1).squeeze(1).view(B, S)
         else:
-            # the CUDA sampler's draw: inverse CDF in natural vocabulary order with ONE uniform per row,
-            # token = first v with cumsum(exp(x*inv_t - max))[v] > u * sum  (same distribution as multinomial)
-            u = philox.uniform_bs(philox_key, step, B, S, stream=0)  # (B, S) fp32 in (0,1)
+            # the CUDA sampler's draw (same distribution as multinomial): a two-level inverse CDF in natural
+            # vocabulary order.  The vocabulary is cut into tiles of 128 entries (what one epilogue thread of the
+            # classifier GEMM holds, csrc/gemm_tcgen05.cu EPI_SAMPLE); uniform 1 picks the tile by its probability
+            # mass, uniform 2 the entry inside it: token = first v in the tile with cumsum(e)[v] > u2 * mass(tile).
+            u1 = philox.uniform_bs(philox_key, step, B, S, stream=0, word=0)  # (B, S) fp32 in (0,1)
+            u2 = philox.uniform_bs(philox_key, step, B, S, stream=0, word=1)
             inv_t = np.float32(1.0 / temperature) if temperature > 0 else np.float32(1.0)
-            xs = logits.numpy().astype(np.float32) * inv_t
-            e = np.exp(xs - xs.max(-1, keepdims=True), dtype=np.float32)
-            cdf = np.cumsum(e, axis=-1, dtype=np.float32)
-            target = u * cdf[..., -1]
-            idx = (cdf > target[..., None]).argmax(-1)
-            none = ~(cdf > target[..., None]).any(-1)
-            idx = np.where(none, logits.numpy().argmax(-1), idx)
-            token = torch.from_numpy(idx.astype(np.int64))
+            TILE = 128
+            assert V % TILE == 0
+            xs = (logits.numpy().astype(np.float32) * inv_t).reshape(B, S, V // TILE, TILE)
+            m_k = xs.max(-1)                                                        # tile maxima
+            e = np.exp(xs - m_k[..., None], dtype=np.float32)
+            cdf_in = np.cumsum(e, axis=-1, dtype=np.float32)                        # within-tile, sequential fp32
+            mass = cdf_in[..., -1] * np.exp(m_k - m_k.max(-1, keepdims=True), dtype=np.float32)
+            cdf_t = np.cumsum(mass, axis=-1, dtype=np.float32)
+            hit_t = cdf_t > (u1 * cdf_t[..., -1])[..., None]
+            k = np.where(hit_t.any(-1), hit_t.argmax(-1), m_k.argmax(-1))           # fallback: tile of the arg-max
+            cdf_k = np.take_along_axis(cdf_in, k[..., None, None], axis=2)[:, :, 0, :]
+            xs_k = np.take_along_axis(xs, k[..., None, None], axis=2)[:, :, 0, :]
+            hit_v = cdf_k > (u2 * cdf_k[..., -1])[..., None]
+            idx = np.where(hit_v.any(-1), hit_v.argmax(-1), xs_k.argmax(-1))        # fallback: arg-max of the tile
+            token = torch.from_numpy((k * TILE + idx).astype(np.int64))
         token_probs = probs.take_along_dim(token.unsqueeze(-1), dim=-1).squeeze(-1)
         return token, token_probs
 

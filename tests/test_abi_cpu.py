@@ -63,11 +63,11 @@ lib.vnb_get_option.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
 lib.vnb_set_option.argtypes = [C.c_char_p, C.c_int32]
 lib.vnb_last_error.restype = C.c_char_p
 out = {}
-for name in (b"gemm_pair",):
+for name in (b"gemm_pair", b"fused_sampler"):
     v = C.c_int32(-7)
     assert lib.vnb_get_option(name, C.byref(v)) == 0, name
     out[name.decode()] = v.value
-assert out == {"gemm_pair": 1}, out
+assert out == {"gemm_pair": 1, "fused_sampler": 1}, out
 assert lib.vnb_set_option(b"gemm_pair", 0) == 0
 v = C.c_int32()
 lib.vnb_get_option(b"gemm_pair", C.byref(v)); assert v.value == 0

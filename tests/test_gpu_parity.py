@@ -74,6 +74,37 @@ def test_forward_vs_oracle_and_golden(golden_dir, tag, cfgd, lora):
     assert torch.equal(got, got2)
 
 
+@pytest.mark.parametrize("tag,cfgd", [("coarse", TINY_COARSE), ("c2f", TINY_C2F)])
+@pytest.mark.parametrize("kw", [dict(), dict(temperature=0.7, sample_cutoff=0.5), dict(sample_cutoff=-1.0, mask_temperature=0.0)])
+def test_fused_sampler_equals_materialised_sampler(tag, cfgd, kw):
+    """vnb_set_option("fused_sampler"): sampling inside the classifier GEMM's epilogue (default) and sampling from the
+    materialised logits tensor draw with the same two-level inverse CDF from the same Philox stream, so the tokens are
+    the same (they could differ only where a uniform lands within rounding of a CDF step).  T = 150 gives two row tiles
+    with a ragged tail; the batch of 3 exercises the (b, t) -> Philox counter mapping."""
+    from vampnet_b200 import _lib as L
+    import ctypes
+    cfg, sd, model, cb, codec = build(cfgd)
+    g = torch.Generator().manual_seed(23)
+    z = torch.randint(0, 1024, (3, cfg.n_codebooks, 150), generator=g).cuda()
+    mask = torch.ones_like(z)
+    mask[:, :, ::5] = 0
+    prev = ctypes.c_int32(0)
+    L.check(L.lib().vnb_get_option(b"fused_sampler", ctypes.byref(prev)))
+    outs = []
+    try:
+        for fused in (1, 0):
+            L.check(L.lib().vnb_set_option(b"fused_sampler", fused))
+            for graph in (False, True):
+                model.use_cuda_graph = graph
+                outs.append(model.generate(codec, start_tokens=z, mask=mask, _sampling_steps=5, seed=17,
+                                           return_signal=False, **kw).cpu())
+    finally:
+        L.check(L.lib().vnb_set_option(b"fused_sampler", prev.value))
+    assert not (outs[0] == cfg.mask_token).any()
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o), f"{(outs[0] != o).sum().item()} of {o.numel()} tokens differ"
+
+
 def _teacher_forced(model, codec):
     """logits_fn for the oracle loop: the product's own forward on the oracle's current state, so both
     samplers see bit-identical logits."""

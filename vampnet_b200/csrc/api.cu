@@ -138,19 +138,22 @@ struct GraphKey {  // graphs bake pointers, so generate() stages z/mask/out in w
   bool has_mask;
   bool top_p;  // selects the sampler kernel variant
   int variant;  // GEMM kernel variant baked into the graph (vnb_set_option "gemm_pair")
+  bool fused;   // sampler fused into the classifier epilogue (vnb_set_option "fused_sampler")
   bool operator<(const GraphKey& o) const {
-    return std::tie(steps, has_mask, top_p, variant) < std::tie(o.steps, o.has_mask, o.top_p, o.variant);
+    return std::tie(steps, has_mask, top_p, variant, fused) < std::tie(o.steps, o.has_mask, o.top_p, o.variant, o.fused);
   }
 };
 
 struct Workspace {
   int B = 0, T = 0, Tpad = 0, M = 0;
   unsigned long long last_use = 0;
-  DevBuf x, y, qk, vT, att, h, logits, zcur, zorig, tokens, conf, n0, dyn, z_in, mask_in, z_out, ssA, ssB, embA;
+  DevBuf x, y, qk, vT, att, h, logits, zcur, zorig, tokens, conf, n0, dyn, z_in, mask_in, z_out, ssA, ssB, embA, partials;
   int embKp = 0;
   int ss_parts = 0;
   std::vector<GemmPlan> qkv, wo, up, down;
   GemmPlan cls, emb;
+  GemmPlan cls_sample;  // the classifier with the sampling epilogue (generate loop)
+  bool can_fuse = false;
   AttnPlan attn;
   std::map<GraphKey, cudaGraphExec_t> graphs;
   std::map<GraphKey, unsigned long long> graph_kernels;
@@ -266,6 +269,18 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
                       m->w.bcls, T, ws->Tpad, 0))
     return fail("plan classifier: %s", tmap_error());
   consumer(ws->cls, ws->ssA);
+  // generate loop: the same GEMM with the sampling epilogue; the logits are consumed in the epilogue and never stored
+  ws->can_fuse = c.vocab_size % 128 == 0 && c.vocab_size <= 1024;
+  if (ws->can_fuse) {
+    CK(ws->partials.alloc(M * static_cast<size_t>(Cp) * (c.vocab_size / 128) * 16));
+    ws->cls_sample = ws->cls;
+    ws->cls_sample.epi = VNB_EPI_SAMPLE;
+    ws->cls_sample.out = nullptr;
+    ws->cls_sample.zcur = ws->zcur.as<int32_t>();
+    ws->cls_sample.partials = ws->partials.p;
+    ws->cls_sample.C = c.n_codebooks; ws->cls_sample.ncc = c.n_conditioning_codebooks;
+    ws->cls_sample.V = c.vocab_size; ws->cls_sample.mask_token = c.vocab_size;
+  }
   // embedding out_proj (layers.py:162) as a split-bf16 tensor-core contraction: x = A . emb_w3^T + bias, which also
   // emits bf16(x) and the row sums of squares the first QKV projection's fused RMSNorm consumes
   if (!make_gemm_plan(&ws->emb, VNB_EPI_BIAS_F32, ws->embA.p, m->w.emb_w3, ws->M, d, 3 * ws->embKp, ws->x.p, nullptr,
@@ -298,7 +313,8 @@ static int run_embed(vnb_model* m, Workspace* ws, const int32_t* codes_btc, cons
 }
 
 // x already holds the embedded input; runs the L layers + final norm + classifier into `logits`.
-static int run_stack(vnb_model* m, Workspace* ws, float* logits, cudaStream_t st, float* acts = nullptr) {
+static int run_stack(vnb_model* m, Workspace* ws, float* logits, cudaStream_t st, float* acts = nullptr,
+                     const SampleDyn* fused_dyn = nullptr) {
   const vnb_config& c = m->cfg;
   // RMSNorm (transformer.py:43-58) is fused: norm weights are folded into wqkv / w1 / wcls at pack time, the
   // producers of x (embed, attn-out, ffn-down) also emit bf16(x) and per-row sums of squares, and the consumers
@@ -312,9 +328,15 @@ static int run_stack(vnb_model* m, Workspace* ws, float* logits, cudaStream_t st
     if (acts)  // return_activations: the residual stream after this layer (transformer.py:455-456)
       CK(cudaMemcpyAsync(acts + static_cast<size_t>(l) * ws->M * c.d_model, ws->x.p, ws->x.n, cudaMemcpyDeviceToDevice, st));
   }
-  GemmPlan cls = ws->cls;
-  cls.out = logits;
-  LAUNCH(FAM_GEMM_CLS, launch_gemm(cls, st));
+  if (fused_dyn != nullptr) {  // generate loop: sample in the classifier's epilogue, no logits tensor
+    GemmPlan cls = ws->cls_sample;
+    cls.dyn = fused_dyn;
+    LAUNCH(FAM_GEMM_CLS, launch_gemm(cls, st));
+  } else {
+    GemmPlan cls = ws->cls;
+    cls.out = logits;
+    LAUNCH(FAM_GEMM_CLS, launch_gemm(cls, st));
+  }
   m->prof.mark(-1, st);
   return 0;
 }
@@ -391,8 +413,19 @@ int32_t vnb_get_hidden(vnb_model* m, float* out, void* stream) {
   return 0;
 }
 
+// vnb_set_option("fused_sampler", 0|1): sample inside the classifier GEMM's epilogue (default) or from a materialised
+// logits tensor.  Nucleus (top-p) filtering needs whole sorted rows and always takes the materialising path.
+static int g_fused_sampler = -1;  // -1: not read yet (environment VNB_FUSED_SAMPLER, else on)
+static int fused_sampler_enabled() {
+  if (g_fused_sampler < 0) {
+    const char* e = getenv("VNB_FUSED_SAMPLER");
+    g_fused_sampler = e != nullptr ? (e[0] != '0') : 1;
+  }
+  return g_fused_sampler;
+}
+
 static int enqueue_generate(vnb_model* m, Workspace* ws, const int64_t* z, const int32_t* mask, int steps, int64_t* out,
-                            cudaStream_t st, bool use_top_p) {
+                            cudaStream_t st, bool use_top_p, bool fused) {
   const vnb_config& c = m->cfg;
   const int ncc = c.n_conditioning_codebooks;
   LAUNCH(FAM_STATE, launch_gen_init(z, mask, ws->zcur.as<int32_t>(), ws->zorig.as<int32_t>(), ws->n0.as<int32_t>(), ws->B, c.n_codebooks,
@@ -407,8 +440,14 @@ static int enqueue_generate(vnb_model* m, Workspace* ws, const int64_t* z, const
   sa.B = ws->B; sa.T = ws->T; sa.C = c.n_codebooks; sa.ncc = ncc; sa.V = c.vocab_size; sa.mask_token = c.vocab_size;
   for (int i = 0; i < steps; ++i) {
     if (run_embed(m, ws, ws->zcur.as<int32_t>(), nullptr, st)) return 1;
-    if (run_stack(m, ws, ws->logits.as<float>(), st)) return 1;
-    LAUNCH(FAM_SAMPLE, launch_sample_step_dev(sa, ws->dyn.as<SampleDyn>() + i, st, use_top_p));
+    const SampleDyn* dyn_i = ws->dyn.as<SampleDyn>() + i;
+    if (fused) {
+      if (run_stack(m, ws, nullptr, st, nullptr, dyn_i)) return 1;
+      LAUNCH(FAM_SAMPLE, launch_sample_combine_dev(sa, ws->partials.p, dyn_i, st));
+    } else {
+      if (run_stack(m, ws, ws->logits.as<float>(), st)) return 1;
+      LAUNCH(FAM_SAMPLE, launch_sample_step_dev(sa, dyn_i, st, use_top_p));
+    }
     ++g_launches;  // sample step = two kernels
   }
   LAUNCH(FAM_STATE, launch_gen_finish(ws->tokens.as<int32_t>(), ws->zorig.as<int32_t>(), out, ws->B, c.n_codebooks, ws->T, ncc, st));
@@ -440,7 +479,8 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   // pageable source: the runtime stages it before returning, so `dyn` may die at scope exit
   CK(cudaMemcpyAsync(ws->dyn.p, dyn.data(), sizeof(SampleDyn) * steps, cudaMemcpyHostToDevice, st));
   const bool use_top_p = p->top_p > 0.f && p->top_p < 1.f;
-  if (!p->use_graph || m->prof.on) return enqueue_generate(m, ws, z, mask, steps, out, st, use_top_p);
+  const bool fused = fused_sampler_enabled() != 0 && !use_top_p && ws->can_fuse;
+  if (!p->use_graph || m->prof.on) return enqueue_generate(m, ws, z, mask, steps, out, st, use_top_p, fused);
 
   const size_t nz = static_cast<size_t>(B) * m->cfg.n_codebooks * T;
   CK(cudaMemcpyAsync(ws->z_in.p, z, nz * 8, cudaMemcpyDeviceToDevice, st));
@@ -448,7 +488,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   const int64_t* gz = ws->z_in.as<int64_t>();
   const int32_t* gmask = mask ? ws->mask_in.as<int32_t>() : nullptr;
   int64_t* gout = ws->z_out.as<int64_t>();
-  GraphKey key{steps, mask != nullptr, use_top_p, get_gemm_pair()};
+  GraphKey key{steps, mask != nullptr, use_top_p, get_gemm_pair(), fused};
   auto it = ws->graphs.find(key);
   if (it == ws->graphs.end()) {
     cudaStream_t cap;
@@ -457,7 +497,7 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
     cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) { cudaStreamDestroy(cap); return fail("begin capture: %s", cudaGetErrorString(e)); }
     const unsigned long long before = g_launches;
-    int rc = enqueue_generate(m, ws, gz, gmask, steps, gout, cap, use_top_p);
+    int rc = enqueue_generate(m, ws, gz, gmask, steps, gout, cap, use_top_p, fused);
     const unsigned long long in_graph = g_launches - before;
     g_launches = before;
     e = cudaStreamEndCapture(cap, &graph);
@@ -492,12 +532,20 @@ int32_t vnb_set_option(const char* name, int32_t value) {
     set_gemm_pair(value);
     return 0;
   }
+  if (strcmp(name, "fused_sampler") == 0) {
+    g_fused_sampler = value ? 1 : 0;
+    return 0;
+  }
   return fail("unknown option '%s'", name);
 }
 int32_t vnb_get_option(const char* name, int32_t* value) {
   if (!name || !value) return fail("null argument");
   if (strcmp(name, "gemm_pair") == 0) {
     *value = get_gemm_pair();
+    return 0;
+  }
+  if (strcmp(name, "fused_sampler") == 0) {
+    *value = fused_sampler_enabled();
     return 0;
   }
   if (strcmp(name, "gemm_pair_max_clusters") == 0) {  // read-only: co-resident CTA pairs on the current device

@@ -405,4 +405,21 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// ---- Philox4x32-10 (Salmon et al.); stream layout documented in oracle/philox.py ----------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// 23 random bits + 0.5: exact in fp32, strictly inside (0,1) (24 bits + 0.5 would round up to 1.0)
+__device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x >> 9) + 0.5f) * 1.1920928955078125e-07f; }
+
 }  // namespace vnb

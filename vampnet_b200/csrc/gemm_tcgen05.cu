@@ -36,7 +36,7 @@ constexpr int RING_BYTES = STAGES * STAGE_BYTES;  // 192 KiB: 4 x {A 16K, W 32K}
 constexpr int GEMM_SMEM = RING_BYTES + GEMM_STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 // The residual epilogue is bound by memory-level parallelism (residual rows must be fetched before they can be
 // updated): it gets 8 epilogue warps, two per TMEM lane quadrant, splitting the 32-column chunks even / odd.
-template <int EPI> constexpr int gemm_epi_warps() { return EPI == VNB_EPI_RESID ? 8 : 4; }
+template <int EPI> constexpr int gemm_epi_warps() { return (EPI == VNB_EPI_RESID || EPI == VNB_EPI_SAMPLE) ? 8 : 4; }
 template <int EPI> constexpr int gemm_threads() { return 128 + 32 * gemm_epi_warps<EPI>(); }
 constexpr int STG_PITCH_RESID = 33;  // scalar, conflict-free; 8 x 32 x 33 floats fit beside the 4-stage ring
 
@@ -54,6 +54,11 @@ struct GemmArgs {
   const float* ss_in;       // consumers: partial row sums of squares of THEIR A operand; null = no row scaling
   int ss_parts;             // number of partials to add (fixed order: deterministic)
   float inv_d, eps;         // row scale = rsqrt(sum * inv_d + eps)
+  // ---- EPI_SAMPLE (see the epilogue) ----
+  const int32_t* zcur;
+  const SampleDyn* dyn;
+  float4* partials;
+  int C, ncc, V, mask_token;
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -353,6 +358,105 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           stage_rows(stg, lane, r);
           drain_bf16(reinterpret_cast<__nv_bfloat16*>(g.out), g.N / 2, g.M, stg, lane, row_base, (n0 >> 1) + c * 32);
         }
+      } else if constexpr (EPI == VNB_EPI_SAMPLE) {
+        // The classifier of the generate loop (transformer.py:632-634 followed by sample_from_logits, :952-1034): the
+        // logits of a still-masked position are consumed where they are produced.  A thread owns one row (tcgen05.ld
+        // hands every lane an accumulator row) and one 128-column strip = one 128-entry tile of one codebook's
+        // vocabulary; three sweeps over the strip in TMEM: max / arg-max, sum of exp((x - max) / temperature), and the
+        // inverse-CDF draw inside the strip with this row's second uniform.  What leaves the SM is 16 bytes per (row,
+        // strip); sample_combine_kernel picks the strip with the first uniform.  Same arithmetic for the logit as the
+        // materialising epilogue (acc * row scale, + bias), so vnb_forward_* shows exactly what was sampled from.
+        constexpr float LOG2E_F = 1.4426950408889634f;
+        const int et = static_cast<int>(threadIdx.x) - 128;              // 0..255 over the eight epilogue warps
+        float* sbias = stg_all + (it & 1) * BN;                          // this tile's bias, double-buffered by tile
+        sbias[et] = __ldg(g.bias + n0 + et);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const int strip = (warp - 4) >> 2;                               // columns [128 strip, 128 strip + 128) of the tile
+        const int col0 = n0 + strip * 128;
+        const int cp = col0 / g.V, v0 = col0 - cp * g.V;
+        const int Cp = g.C - g.ncc;
+        const bool active = row_ok && __ldg(g.zcur + static_cast<size_t>(row) * g.C + g.ncc + cp) == g.mask_token;
+        if (__any_sync(0xffffffffu, active)) {
+          const uint32_t t_strip = t_addr + strip * 128;
+          const float4* sb4 = reinterpret_cast<const float4*>(sbias + strip * 128);
+          const float inv_temp = g.dyn->inv_temp;
+          const int do_sample = g.dyn->do_sample;
+          // sweep 1: maximum and arg-max (lowest index on ties) of the logits
+          float mx = -INFINITY;
+          int am = 0;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_x32(t_strip + c * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = sb4[c * 8 + j4];
+              const float bj[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float x = __fadd_rn(__fmul_rn(__uint_as_float(v[j4 * 4 + j]), rs), bj[j]);
+                if (x > mx) { mx = x; am = c * 32 + j4 * 4 + j; }
+              }
+            }
+          }
+          // sweep 2: s = sum over the strip of e = 2^((x - mx) * c1), c1 = log2(e) / temperature, in column order
+          const float c1 = __fmul_rn(inv_temp, LOG2E_F);
+          const float c0 = -__fmul_rn(mx, c1);
+          float ssum = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_x32(t_strip + c * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = sb4[c * 8 + j4];
+              const float bj[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float x = __fadd_rn(__fmul_rn(__uint_as_float(v[j4 * 4 + j]), rs), bj[j]);
+                ssum += fast_exp2(__fmaf_rn(x, c1, c0));
+              }
+            }
+          }
+          // sweep 3 (sampling steps only): first column whose running sum exceeds u2 * s; the arg-max if rounding
+          // leaves none.  Greedy steps take the arg-max.
+          int cand = am;
+          float xc = mx;
+          if (do_sample) {
+            const int b_idx = row / g.T, t_idx = row - b_idx * g.T;
+            uint32_t r4[4];
+            philox4x32_10(static_cast<uint32_t>(t_idx * Cp + cp), static_cast<uint32_t>(b_idx),
+                          static_cast<uint32_t>(g.dyn->step), 0u, g.dyn->seed_lo, g.dyn->seed_hi, r4);
+            const float target = u01(r4[1]) * ssum;
+            float run = 0.f;
+            int found = -1;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t v[32];
+              tmem_ld_x32(t_strip + c * 32, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 b4 = sb4[c * 8 + j4];
+                const float bj[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float x = __fadd_rn(__fmul_rn(__uint_as_float(v[j4 * 4 + j]), rs), bj[j]);
+                  run += fast_exp2(__fmaf_rn(x, c1, c0));
+                  if (run > target && found < 0) { found = c * 32 + j4 * 4 + j; xc = x; }
+                }
+              }
+            }
+            if (found >= 0) cand = found;
+            else xc = mx;
+          }
+          if (active)
+            g.partials[(static_cast<size_t>(row) * Cp + cp) * (g.V >> 7) + (v0 >> 7)] =
+                make_float4(mx, ssum, xc, __uint_as_float(static_cast<uint32_t>(v0 + cand) |
+                                                          (static_cast<uint32_t>(v0 + am) << 16)));
+        }
       } else if constexpr (EPI == VNB_EPI_RESID || EPI == VNB_EPI_BIAS_F32) {
         // software-pipelined: the residual rows of chunk c+1 are in flight while chunk c is pulled out of TMEM,
         // transposed and stored (the global-load latency would otherwise be paid 8 times per tile, serially)
@@ -475,7 +579,7 @@ int get_gemm_pair() { return gemm_pair_enabled() ? 1 : 0; }
 // Once per device and epilogue: opt in to the large dynamic shared memory for both tile variants and ask how many CTA
 // pairs can be co-resident (one CTA per SM, both SMs of a TPC).  Called eagerly by prepare_gemm() (model creation), so
 // that none of this runs inside a stream capture.
-static int g_max_clusters[5][64];
+static int g_max_clusters[6][64];
 template <int EPI>
 static cudaError_t init_epi() {
   static PerDeviceOnce once;
@@ -506,7 +610,8 @@ cudaError_t prepare_gemm() {
   if ((e = init_epi<VNB_EPI_QKV>()) != cudaSuccess) return e;
   if ((e = init_epi<VNB_EPI_RESID>()) != cudaSuccess) return e;
   if ((e = init_epi<VNB_EPI_GEGLU>()) != cudaSuccess) return e;
-  return init_epi<VNB_EPI_BIAS_F32>();
+  if ((e = init_epi<VNB_EPI_BIAS_F32>()) != cudaSuccess) return e;
+  return init_epi<VNB_EPI_SAMPLE>();
 }
 
 int get_gemm_max_clusters() {
@@ -550,12 +655,17 @@ cudaError_t launch_gemm(const GemmPlan& p, cudaStream_t st) {
   g.T = p.T; g.Tpad = p.Tpad; g.d2 = p.d2;
   g.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p.out_bf16); g.ss_out = p.ss_out; g.ss_in = p.ss_in;
   g.ss_parts = p.ss_parts; g.inv_d = p.inv_d; g.eps = p.eps;
+  g.zcur = p.zcur; g.dyn = p.dyn; g.partials = reinterpret_cast<float4*>(p.partials);
+  g.C = p.C; g.ncc = p.ncc; g.V = p.V; g.mask_token = p.mask_token;
   switch (p.epi) {
     case VNB_EPI_BF16: return launch_epi<VNB_EPI_BF16>(p, g, st);
     case VNB_EPI_QKV: return launch_epi<VNB_EPI_QKV>(p, g, st);
     case VNB_EPI_RESID: return launch_epi<VNB_EPI_RESID>(p, g, st);
     case VNB_EPI_GEGLU: return launch_epi<VNB_EPI_GEGLU>(p, g, st);
     case VNB_EPI_BIAS_F32: return launch_epi<VNB_EPI_BIAS_F32>(p, g, st);
+    case VNB_EPI_SAMPLE:
+      if (!p.zcur || !p.dyn || !p.partials || !p.bias || p.V % 128 != 0 || p.V > 1024) return cudaErrorInvalidValue;
+      return launch_epi<VNB_EPI_SAMPLE>(p, g, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -44,6 +44,8 @@ const char* tmap_error();
 extern "C" int32_t vnb_set_error_cuda(const char* what, int32_t cuda_error);
 namespace vnb {
 
+struct SampleDyn;
+
 // ---- GEMM ----
 struct GemmPlan {
   CUtensorMap tmA, tmB;
@@ -59,6 +61,11 @@ struct GemmPlan {
   const float* ss_in = nullptr;
   int ss_parts = 0;
   float inv_d = 0.f, eps = 0.f;
+  // VNB_EPI_SAMPLE (the classifier of the generate loop): the logits are sampled in the epilogue instead of being stored
+  const int32_t* zcur = nullptr;     // (B, T, C) current tokens: only still-masked positions are sampled
+  const SampleDyn* dyn = nullptr;    // this step's scalars (device memory: graph replay safe)
+  void* partials = nullptr;          // (M * Cp * V/128) float4 records, see sample_combine_kernel
+  int C = 0, ncc = 0, V = 0, mask_token = 0;
 };
 // Fills the tensor maps; A (M,K) bf16, W (N,K) bf16.
 bool make_gemm_plan(GemmPlan* p, int epi, const void* A, const void* W, int M, int N, int K, void* out, void* out2,
@@ -118,5 +125,7 @@ struct SampleArgs {
 };
 // use_top_p selects the kernel variant at launch time (it is baked into a captured graph: part of the graph key)
 cudaError_t launch_sample_step_dev(const SampleArgs& a, const SampleDyn* dyn_dev, cudaStream_t st, bool use_top_p);
+// fused path: the classifier's sampling epilogue wrote `partials`; picks the tile, writes tokens + confidences, re-masks
+cudaError_t launch_sample_combine_dev(const SampleArgs& a, const void* partials, const SampleDyn* dyn_dev, cudaStream_t st);
 
 }  // namespace vnb

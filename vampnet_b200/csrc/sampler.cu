@@ -16,22 +16,6 @@
 
 namespace vnb {
 
-// ---- Philox4x32-10 (Salmon et al.); stream layout documented in oracle/philox.py ----------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t (&out)[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-// 23 random bits + 0.5: exact in fp32, strictly inside (0,1) (24 bits + 0.5 would round up to 1.0)
-__device__ __forceinline__ float u01(uint32_t x) { return (static_cast<float>(x >> 9) + 0.5f) * 1.1920928955078125e-07f; }
 __device__ __forceinline__ float gumbel(float u) { return -logf(-logf(u)); }
 
 using SampleDynDev = SampleDyn;
@@ -175,7 +159,11 @@ __global__ void __launch_bounds__(256, TOPP ? 2 : 3) sample_rows_kernel(const Sa
     uint32_t r[4];
     philox4x32_10(static_cast<uint32_t>(s), static_cast<uint32_t>(b), static_cast<uint32_t>(dyn.step), 0u, dyn.seed_lo,
                   dyn.seed_hi, r);
-    const float target = u01(r[0]) * se;  // token = first v with cumsum(e)[v] > target
+    // Two-level inverse CDF (oracle/vampnet_oracle.py sample_from_logits, rng="philox"): uniform 1 picks the
+    // 128-entry tile (= chunk i of this layout) by its mass, uniform 2 the entry inside it.  The classifier GEMM's
+    // sampling epilogue (gemm_tcgen05.cu, EPI_SAMPLE) draws the same way from its own 128-column strips.
+    const float target = u01(r[0]) * se;  // tile = first i with cumsum(tile mass)[i] > target
+    const float u2 = u01(r[1]);
     float base = 0.f;
     int pick = -1;
 #pragma unroll
@@ -183,6 +171,7 @@ __global__ void __launch_bounds__(256, TOPP ? 2 : 3) sample_rows_kernel(const Sa
       if (i < n4 && pick < 0) {
         const float tot = warp_sum(csum[i]);
         if (base + tot > target) {
+          const float target_in = u2 * tot;  // token = first v of the tile with cumsum(e)[v] > target_in
           // inclusive scan of the lane sums of this chunk (Hillis-Steele)
           float inc = csum[i];
 #pragma unroll
@@ -190,21 +179,34 @@ __global__ void __launch_bounds__(256, TOPP ? 2 : 3) sample_rows_kernel(const Sa
             const float t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
           }
-          const float before = base + (inc - csum[i]);
+          const float before = inc - csum[i];
           int cand = 0x7fffffff;
-          if (base + inc > target) {  // the crossing is at or before this lane's last entry
+          if (inc > target_in) {  // the crossing is at or before this lane's last entry
             float run = before;
-            int last_pos = -1;  // last entry of this lane with non-zero mass (never pick a filtered-out token)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               run += e[i][j];
-              if (e[i][j] > 0.f) last_pos = j;
-              if (run > target && cand == 0x7fffffff) cand = (i * 32 + lane) * 4 + j;
+              if (run > target_in && cand == 0x7fffffff) cand = (i * 32 + lane) * 4 + j;
             }
-            if (cand == 0x7fffffff && last_pos >= 0) cand = (i * 32 + lane) * 4 + last_pos;
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+          if (cand == 0x7fffffff) {
+            // rounding left target_in >= the tile's mass: the tile's largest entry (lowest index on ties)
+            float tb = -INFINITY;
+            int ti = 0x7fffffff;
+            const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (xs[j] > tb) { tb = xs[j]; ti = (i * 32 + lane) * 4 + j; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ob = __shfl_xor_sync(0xffffffffu, tb, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, ti, o);
+              if (ob > tb || (ob == tb && oi < ti)) { tb = ob; ti = oi; }
+            }
+            cand = ti;
+          }
           pick = cand;
         }
         base += tot;
@@ -316,14 +318,104 @@ __global__ void __launch_bounds__(1024) remask_kernel(const SampleStatic a, cons
   }
 }
 
-cudaError_t launch_sample_step_dev(const SampleArgs& s, const SampleDyn* dyn_dev, cudaStream_t st, bool use_top_p) {
+// Second half of the fused path.  The classifier GEMM's sampling epilogue (gemm_tcgen05.cu, EPI_SAMPLE) left one
+// 16-byte record per (row, 128-entry vocabulary tile): {tile max of the logits, sum of exp((x - max) / temperature),
+// logit of the tile's candidate, candidate | arg-max << 16 (vocabulary indices)}; the candidate was drawn inside the tile
+// with uniform 2.  One thread per row: pick the tile with uniform 1 by mass, take its candidate, and compute
+// confidence = log softmax(token) + temperature * Gumbel exactly as sample_rows_kernel does.  The logits themselves
+// never reach HBM.  Algorithmic bytes: 16 * V/128 per masked row.
+__global__ void __launch_bounds__(256) sample_combine_kernel(const SampleStatic a, const float4* __restrict__ partials,
+                                                             const SampleDynDev* __restrict__ dynp) {
+  const SampleDynDev dyn = *dynp;
+  const int Cp = a.C - a.ncc;
+  const int S = a.T * Cp;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= a.B * S) return;
+  const int b = row / S, s = row - b * S;
+  const int t = s / Cp, cp = s - t * Cp;
+  const int zi = a.zcur[(static_cast<size_t>(b) * a.T + t) * a.C + a.ncc + cp];
+  if (zi != a.mask_token) {  // known token: kept, never re-masked (transformer.py:893-900)
+    a.tokens[row] = zi;
+    a.conf[row] = INFINITY;
+    return;
+  }
+  constexpr int MAXT = 8;
+  const int nt = a.V >> 7;
+  float4 rec[MAXT];
+  float M = -INFINITY;
+  int kmax = 0;
+#pragma unroll
+  for (int k = 0; k < MAXT; ++k) {
+    if (k < nt) {
+      rec[k] = __ldg(partials + static_cast<size_t>(row) * nt + k);
+      if (rec[k].x > M) { M = rec[k].x; kmax = k; }
+    }
+  }
+  const float c1 = __fmul_rn(dyn.inv_temp, 1.4426950408889634f);
+  float mass[MAXT], total = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXT; ++k) {
+    mass[k] = 0.f;
+    if (k < nt) {
+      mass[k] = rec[k].y * fast_exp2(__fmul_rn(rec[k].x - M, c1));
+      total += mass[k];
+    }
+  }
+  int kk = kmax;
+  if (dyn.do_sample) {
+    uint32_t r[4];
+    philox4x32_10(static_cast<uint32_t>(s), static_cast<uint32_t>(b), static_cast<uint32_t>(dyn.step), 0u, dyn.seed_lo,
+                  dyn.seed_hi, r);
+    const float target = u01(r[0]) * total;
+    float run = 0.f;
+    int pick = -1;
+#pragma unroll
+    for (int k = 0; k < MAXT; ++k) {
+      if (k < nt) {
+        run += mass[k];
+        if (run > target && pick < 0) pick = k;
+      }
+    }
+    if (pick >= 0) kk = pick;
+  }
+  float xc = 0.f;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < MAXT; ++k)
+    if (k == kk) { xc = rec[k].z; bits = __float_as_uint(rec[k].w); }
+  const int token = dyn.do_sample ? static_cast<int>(bits & 0xffffu) : static_cast<int>(bits >> 16);
+  const float p = fast_exp2(__fmul_rn(xc - M, c1)) / total;
+  uint32_t r[4];
+  philox4x32_10(static_cast<uint32_t>(s), static_cast<uint32_t>(b), static_cast<uint32_t>(dyn.step), 1u, dyn.seed_lo,
+                dyn.seed_hi, r);
+  a.tokens[row] = token;
+  a.conf[row] = __fadd_rn(logf(p), __fmul_rn(dyn.temp_eff, gumbel(u01(r[0]))));
+}
+
+static SampleStatic make_static(const SampleArgs& s) {
   SampleStatic a;
   a.logits = s.logits; a.zcur = s.zcur; a.zorig = s.zorig; a.tokens = s.tokens; a.conf = s.conf; a.n0 = s.n0;
   a.B = s.B; a.T = s.T; a.C = s.C; a.ncc = s.ncc; a.V = s.V; a.mask_token = s.mask_token;
+  return a;
+}
+
+cudaError_t launch_sample_step_dev(const SampleArgs& s, const SampleDyn* dyn_dev, cudaStream_t st, bool use_top_p) {
+  const SampleStatic a = make_static(s);
   if (s.V % 128 != 0 || s.V > 1024) return cudaErrorInvalidValue;
   const int rows = s.B * s.T * (s.C - s.ncc);
   if (use_top_p) sample_rows_kernel<true><<<(rows + 7) / 8, 256, 0, st>>>(a, dyn_dev);
   else sample_rows_kernel<false><<<(rows + 7) / 8, 256, 0, st>>>(a, dyn_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  remask_kernel<<<s.B, 1024, 0, st>>>(a, dyn_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample_combine_dev(const SampleArgs& s, const void* partials, const SampleDyn* dyn_dev, cudaStream_t st) {
+  const SampleStatic a = make_static(s);
+  if (s.V % 128 != 0 || s.V > 1024) return cudaErrorInvalidValue;
+  const int rows = s.B * s.T * (s.C - s.ncc);
+  sample_combine_kernel<<<(rows + 255) / 256, 256, 0, st>>>(a, reinterpret_cast<const float4*>(partials), dyn_dev);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   remask_kernel<<<s.B, 1024, 0, st>>>(a, dyn_dev);
