@@ -25,8 +25,11 @@ for cfg in (dict(n_heads=4, n_layers=2, n_codebooks=4, n_conditioning_codebooks=
         mask[:, :, ::5] = 0
         for graph in (False, True):
             m.use_cuda_graph = graph
-            out = m.generate(codec, start_tokens=z, mask=mask, _sampling_steps=3, return_signal=False, seed=1, top_p=0.9)
-        assert not (out == 1024).any()
+            # top-p samples from materialised logits (sample_rows_kernel); without it the classifier GEMM's sampling
+            # epilogue + sample_combine_kernel run
+            for kw in (dict(top_p=0.9), dict(), dict(sample_cutoff=0.5)):
+                out = m.generate(codec, start_tokens=z, mask=mask, _sampling_steps=3, return_signal=False, seed=1, **kw)
+                assert not (out == 1024).any()
     m(torch.randn(2, cfg["n_codebooks"] * 8, 19, device=dev))
 for prec in ("tc", "fp32"):
     dac = DAC(encoder_dim=32, decoder_dim=512, precision=prec).to(dev)
