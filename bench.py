@@ -584,7 +584,7 @@ def main():
             "tflops": world * flops_step * args.steps / (ms * 1e-3) / 1e12,
             "config": {"workload": cfg["workload"], "baseline_config_index": args.config,
                        "global_batch": world * B, "per_gpu_batch": B, "seq_len": T, "parallelism": f"dp{world} (clips)",
-                       "l2": "working set per step (1.3-2.4 GB bf16 weights + logits) far exceeds the 126 MB L2",
+                       "l2": "working set per step (1.3-2.4 GB of bf16 weights, plus ~1 GB of activations per layer) far exceeds the 126 MB L2",
                        "weights": "random-init, NCCL-broadcast from rank 0", "cuda_graph": True},
             "clocks": clk,
             "e2e": {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d * world,
