@@ -5,13 +5,16 @@
 // One kernel family covers every dense contraction of VampNet.forward (reference
 // vampnet/modules/transformer.py): QKV projection (:229-231), attention output projection (:255),
 // FFN up-projection with the GatedGELU fused (:81-83, activations.py:16-35), FFN down-projection
-// with the residual add fused (:84, :367) and the classifier (:632).
+// with the residual add fused (:84, :367), the classifier (:632) and, in the generate loop, the classifier with
+// sample_from_logits (:952-1034) fused into its epilogue (EPI_SAMPLE), and the embedding out_proj (layers.py:162).
 //
-// Structure (one CTA per SM, persistent over output tiles of 128 x 256):
-//   warp 0       TMA producer   : 4-stage ring of {A 128x64, W 256x64} bf16 tiles, 128B-swizzled
-//   warp 1       MMA issuer     : one elected thread, tcgen05.mma M=128 N=256 K=16, 4 per k-block
+// Structure (one CTA per SM, persistent over output tiles; default: CTA pairs on 256 x 256 tiles, see the note above the
+// kernel; single-CTA variant: 128 x 256):
+//   warp 0       TMA producer   : ring of {A 128x64, W 256x64 (pair: W half 128x64)} bf16 tiles, 128B-swizzled, 4 / 6 stages
+//   warp 1       MMA issuer     : one elected thread, tcgen05.mma (.cta_group::2) M=128 (256) N=256 K=16, 4 per k-block
 //   warp 2       TMEM allocator : 512 columns = two 128x256 fp32 accumulators (double buffered)
-//   warps 4..7   epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> fused op -> global
+//   warps 4..    epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> fused op -> global (4 warps; 8 for the
+//                                 residual and the sampling epilogues)
 // The epilogue of tile i overlaps the mainloop of tile i+1 through the two accumulators.
 //
 // Roofline: tensor-bound.  Algorithmic work = 2*M*N*K flop per launch; bytes (A+W+out) are a few

@@ -3,14 +3,18 @@
 // result is discarded by the reference and so is absent here), the where()s that keep known tokens,
 // the cosine-schedule count (:903-913, mask.py:8-9) and mask_by_random_topk (:1038-1074).
 //
-// Two kernels, both HBM-bound:
-//   sample_rows_kernel   one warp per (batch, position): reads the 1024 logits of a STILL-MASKED
-//                        position once (32 per lane, float4), warp-shuffle max / sum-exp, categorical draw by
-//                        inverse CDF with ONE counter-based Philox uniform per row, writes token + confidence.
-//                        Known positions cost 4 bytes.  Algorithmic bytes: V*4 per masked position.
-//   remask_kernel        one CTA per batch row: exact k-th order statistic of the S confidences by a
-//                        4-pass radix select (what sort()[k] yields in the reference), then
-//                        z <- where(conf < cut, MASK, token).
+// In the generate loop the draw itself happens inside the classifier GEMM's epilogue (gemm_tcgen05.cu, EPI_SAMPLE: the
+// logits never reach HBM); what runs here afterwards:
+//   sample_combine_kernel  one thread per (batch, position): picks the 128-entry vocabulary tile from the per-tile
+//                          records the epilogue left (uniform 1), takes that tile's candidate, writes token + confidence.
+//   remask_kernel          one CTA per batch row: exact k-th order statistic of the S confidences by a 4-pass radix
+//                          select (what sort()[k] yields in the reference), then z <- where(conf < cut, MASK, token).
+// With nucleus (top-p) sampling, with vnb_set_option("fused_sampler", 0) and through vnb_sample_step the logits are a
+// tensor and the draw is
+//   sample_rows_kernel     one warp per (batch, position): reads the 1024 logits of a STILL-MASKED position once (32 per
+//                          lane, float4), warp-shuffle max / sum-exp, the same two-level inverse-CDF draw with two
+//                          counter-based Philox uniforms per row, writes token + confidence.  Known positions cost
+//                          4 bytes.  Algorithmic bytes: V*4 per masked position.
 #include "common.cuh"
 #include "kernels.h"
 
