@@ -231,7 +231,8 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
   CK(ws->vT.alloc(static_cast<size_t>(B) * d * ws->Tpad * 2, /*zero=*/true));  // padding keys stay 0 forever
   CK(ws->att.alloc(M * d * 2));
   CK(ws->h.alloc(M * 2 * d * 2));
-  CK(ws->logits.alloc(M * static_cast<size_t>(Cp) * c.vocab_size * 4));
+  // ws->logits (M x Cp*V fp32, 0.4-1 GB at the bench shapes) is only needed when generate() samples from a materialised
+  // tensor (top-p, fused_sampler = 0): allocated on first use in vnb_generate
   CK(ws->zcur.alloc(M * c.n_codebooks * 4));
   CK(ws->zorig.alloc(M * c.n_codebooks * 4));
   CK(ws->tokens.alloc(M * Cp * 4));
@@ -265,7 +266,7 @@ static int get_workspace(vnb_model* m, int B, int T, Workspace** out) {
     consumer(ws->up[l], ws->ssB);
     if (!producer(ws->wo[l], ws->ssB) || !producer(ws->down[l], ws->ssA)) return fail("plan layer %d: %s", l, tmap_error());
   }
-  if (!make_gemm_plan(&ws->cls, VNB_EPI_BIAS_F32, ws->y.p, m->w.wcls, ws->M, Cp * c.vocab_size, d, ws->logits.p, nullptr,
+  if (!make_gemm_plan(&ws->cls, VNB_EPI_BIAS_F32, ws->y.p, m->w.wcls, ws->M, Cp * c.vocab_size, d, nullptr, nullptr,
                       m->w.bcls, T, ws->Tpad, 0))
     return fail("plan classifier: %s", tmap_error());
   consumer(ws->cls, ws->ssA);
@@ -480,6 +481,8 @@ int32_t vnb_generate(vnb_model* m, const int64_t* z, const int32_t* mask, int32_
   CK(cudaMemcpyAsync(ws->dyn.p, dyn.data(), sizeof(SampleDyn) * steps, cudaMemcpyHostToDevice, st));
   const bool use_top_p = p->top_p > 0.f && p->top_p < 1.f;
   const bool fused = fused_sampler_enabled() != 0 && !use_top_p && ws->can_fuse;
+  if (!fused && ws->logits.p == nullptr)  // before any capture: cudaMalloc is not capturable
+    CK(ws->logits.alloc(static_cast<size_t>(ws->M) * (m->cfg.n_codebooks - m->cfg.n_conditioning_codebooks) * m->cfg.vocab_size * 4));
   if (!p->use_graph || m->prof.on) return enqueue_generate(m, ws, z, mask, steps, out, st, use_top_p, fused);
 
   const size_t nz = static_cast<size_t>(B) * m->cfg.n_codebooks * T;
