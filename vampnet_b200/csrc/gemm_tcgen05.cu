@@ -81,15 +81,17 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 constexpr int STG_PITCH = 36;
 constexpr int STG_FLOATS_PER_WARP = 32 * STG_PITCH;
 
-__device__ __forceinline__ void stage_rows(float* stg, int lane, const float (&v)[32]) {
-  float4* dst = reinterpret_cast<float4*>(stg + lane * STG_PITCH);
+// `stg` is a shared-space byte address (smem_u32): the tile base passes through an integer alignment, which would make
+// plain pointers generic (LD.E / ST.E instead of LDS / STS).
+__device__ __forceinline__ void stage_rows(uint32_t stg, int lane, const float (&v)[32]) {
+  const uint32_t dst = stg + 4u * (lane * STG_PITCH);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int i = 0; i < 8; ++i) sts_f4(dst + 16u * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
   __syncwarp();
 }
-__device__ __forceinline__ void stage_rows33(float* stg, int lane, const float (&v)[32]) {
+__device__ __forceinline__ void stage_rows33(uint32_t stg, int lane, const float (&v)[32]) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) stg[lane * STG_PITCH_RESID + j] = v[j];
+  for (int j = 0; j < 32; ++j) sts_f32(stg + 4u * (lane * STG_PITCH_RESID + j), v[j]);
   __syncwarp();
 }
 
@@ -121,7 +123,7 @@ __device__ __forceinline__ void prefetch_addend(const GemmArgs& g, int lane, int
   }
 }
 template <bool FUSED, int PITCH>
-__device__ __forceinline__ void drain_f32(const GemmArgs& g, const float* stg, int lane, int row_base, int col0,
+__device__ __forceinline__ void drain_f32(const GemmArgs& g, uint32_t stg, int lane, int row_base, int col0,
                                           const float4 (&add)[8], float (&ssacc)[8]) {
   const int c4 = (lane & 7) * 4;
   const int r0 = row_base + (lane >> 3);
@@ -129,8 +131,8 @@ __device__ __forceinline__ void drain_f32(const GemmArgs& g, const float* stg, i
   const size_t step = static_cast<size_t>(4) * g.N;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const float* sp = stg + (it * 4 + (lane >> 3)) * PITCH + c4;
-    float4 a = make_float4(sp[0], sp[1], sp[2], sp[3]);
+    const uint32_t sp = stg + 4u * ((it * 4 + (lane >> 3)) * PITCH + c4);
+    float4 a = (PITCH % 4 == 0) ? lds_f4(sp) : make_float4(lds_f32(sp), lds_f32(sp + 4), lds_f32(sp + 8), lds_f32(sp + 12));
     a.x = __fadd_rn(a.x, add[it].x); a.y = __fadd_rn(a.y, add[it].y);
     a.z = __fadd_rn(a.z, add[it].z); a.w = __fadd_rn(a.w, add[it].w);
     if (r0 + it * 4 < g.M) {
@@ -148,7 +150,7 @@ __device__ __forceinline__ void drain_f32(const GemmArgs& g, const float* stg, i
 }
 
 // bf16 destinations: lane -> (row = it*8 + lane/4, 8 columns at (lane%4)*8); `pitch` = output row pitch
-__device__ __forceinline__ void drain_bf16(__nv_bfloat16* out, int pitch, int M, const float* stg, int lane,
+__device__ __forceinline__ void drain_bf16(__nv_bfloat16* out, int pitch, int M, uint32_t stg, int lane,
                                            int row_base, int col0) {
   const int c8 = (lane & 3) * 8;
 #pragma unroll
@@ -156,8 +158,8 @@ __device__ __forceinline__ void drain_bf16(__nv_bfloat16* out, int pitch, int M,
     const int r = it * 8 + (lane >> 2);
     const int row = row_base + r;
     if (row < M) {
-      const float4 a = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c8);
-      const float4 b = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + c8 + 4);
+      const float4 a = lds_f4(stg + 4u * (r * STG_PITCH + c8));
+      const float4 b = lds_f4(stg + 4u * (r * STG_PITCH + c8 + 4));
       uint4 w;
       w.x = pack_bf16x2(a.x, a.y);
       w.y = pack_bf16x2(a.z, a.w);
@@ -334,7 +336,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       constexpr bool kWide = gemm_epi_warps<EPI>() == 8;
       const int half = kWide ? ((warp - 4) >> 2) : 0;  // 8-warp epilogue: this warp takes chunks with (c & 1) == half
-      float* stg = kWide ? stg_all + (warp - 4) * (32 * STG_PITCH_RESID) : stg_all + quad * STG_FLOATS_PER_WARP;
+      const uint32_t stg = smem_u32(kWide ? stg_all + (warp - 4) * (32 * STG_PITCH_RESID) : stg_all + quad * STG_FLOATS_PER_WARP);
       const int row_base = m0 + quad * 32;
       float rs = 1.0f;  // fused RMSNorm of the A operand: rsqrt(mean(x^2) + eps) of this thread's row
       if (g.ss_in != nullptr && row_ok) {
@@ -371,8 +373,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // materialising epilogue (acc * row scale, + bias), so vnb_forward_* shows exactly what was sampled from.
         constexpr float LOG2E_F = 1.4426950408889634f;
         const int et = static_cast<int>(threadIdx.x) - 128;              // 0..255 over the eight epilogue warps
-        float* sbias = stg_all + (it & 1) * BN;                          // this tile's bias, double-buffered by tile
-        sbias[et] = __ldg(g.bias + n0 + et);
+        const uint32_t sbias = smem_u32(stg_all + (it & 1) * BN);        // this tile's bias, double-buffered by tile
+        sts_f32(sbias + 4u * et, __ldg(g.bias + n0 + et));
         asm volatile("bar.sync 2, 256;" ::: "memory");
         const int strip = (warp - 4) >> 2;                               // columns [128 strip, 128 strip + 128) of the tile
         const int col0 = n0 + strip * 128;
@@ -381,7 +383,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool active = row_ok && __ldg(g.zcur + static_cast<size_t>(row) * g.C + g.ncc + cp) == g.mask_token;
         if (__any_sync(0xffffffffu, active)) {
           const uint32_t t_strip = t_addr + strip * 128;
-          const float4* sb4 = reinterpret_cast<const float4*>(sbias + strip * 128);
+          const uint32_t sb4 = sbias + 4u * (strip * 128);
           const float inv_temp = g.dyn->inv_temp;
           const int do_sample = g.dyn->do_sample;
           // sweep 1: maximum and arg-max (lowest index on ties) of the logits
@@ -394,7 +396,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tmem_wait_ld();
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b4 = sb4[c * 8 + j4];
+              const float4 b4 = lds_f4(sb4 + 16u * (c * 8 + j4));
               const float bj[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -414,7 +416,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tmem_wait_ld();
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b4 = sb4[c * 8 + j4];
+              const float4 b4 = lds_f4(sb4 + 16u * (c * 8 + j4));
               const float bj[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -442,7 +444,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tmem_wait_ld();
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 b4 = sb4[c * 8 + j4];
+                const float4 b4 = lds_f4(sb4 + 16u * (c * 8 + j4));
                 const float bj[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
